@@ -1,0 +1,134 @@
+/*
+ * nightlight_cuda.h -- C ABI of libnightlight_cuda.so, the B200 (sm_100a) implementation of
+ * mlnoga/nightlight's data-parallel stacking hot path.
+ *
+ * The reference has no FFI of its own: the seam is three Go call sites.
+ * Every entry point below names the reference interface it replaces (file:line relative to the
+ * reference root) and is what a cgo / ctypes binding for that call site binds
+ * (INTEGRATION.md shows the cgo stubs).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns NL_OK (0) or a negative NL_E_* code; nl_last_error() returns the
+ *     calling thread's message for the last failure;
+ *   - "host" pointers are ordinary (pageable or pinned) CPU memory, "dev" pointers are CUDA device
+ *     memory on the context's device;
+ *   - a context owns one CUDA device and one stream; calls on one context are serialised on that
+ *     stream, different contexts are independent (one context per goroutine / thread / rank);
+ *   - there is no CPU fallback: without a CUDA device nl_ctx_create fails with NL_E_CUDA.
+ */
+#ifndef NIGHTLIGHT_CUDA_H
+#define NIGHTLIGHT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NL_OK            0
+#define NL_E_INVALID    (-1)   /* bad argument; for stacking: "invalid stacking mode" (stack.go:118-120) */
+#define NL_E_CUDA       (-2)   /* CUDA runtime / driver error, or no device */
+#define NL_E_UNSUPPORTED (-3)  /* MAD sigma with weights: the reference panics there (stack.go:185) */
+#define NL_E_SINGULAR   (-4)   /* "Matrix has no inverse" (coord.go:160-163) */
+#define NL_E_NOMEM      (-5)
+#define NL_E_WEIGHTS    (-6)   /* getWeights error (stack.go:231-270), e.g. missing exposure */
+
+/* Stacking modes, numbered like the reference's StackMode (internal/ops/stack/stack.go:33-42). */
+enum {
+    NL_ST_MEDIAN = 0, NL_ST_MEAN = 1, NL_ST_SIGMA = 2, NL_ST_WINSOR_SIGMA = 3,
+    NL_ST_MAD_SIGMA = 4, NL_ST_LINEAR_FIT = 5, NL_ST_AUTO = 6
+};
+/* Weighting modes, like StackWeighting (stack.go:57-63). */
+enum { NL_W_NONE = 0, NL_W_EXPOSURE = 1, NL_W_INVERSE_NOISE = 2, NL_W_INVERSE_HFR = 3 };
+
+typedef struct nl_ctx nl_ctx;
+typedef struct nl_stack_job nl_stack_job;
+
+/* star.Star (internal/star/findstars.go:30-37), same field order and types. */
+typedef struct {
+    int32_t index;
+    float   value;
+    float   x, y;
+    float   mass;
+    float   hfr;
+} nl_star;
+
+/* ---- library / context ------------------------------------------------------------------- */
+const char *nl_last_error(void);
+int  nl_version(void);                            /* 10000*major + 100*minor + patch */
+int  nl_device_count(int *count);
+int  nl_ctx_create(int device, nl_ctx **ctx);     /* one device + one stream */
+int  nl_ctx_destroy(nl_ctx *ctx);
+int  nl_ctx_sync(nl_ctx *ctx);                    /* wait for the context's stream */
+int  nl_ctx_stream(nl_ctx *ctx, void **stream);   /* the cudaStream_t, for event timing by the caller */
+int  nl_ctx_device(nl_ctx *ctx, int *device);
+/* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
+int  nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches);
+
+/* ---- stacking: replaces OpStack.Apply + Stack* (internal/ops/stack/stack.go:115-227, 274-918) --
+ * A job holds the N frames (or one row stripe of them: `pixels` = stripe pixels) in device memory,
+ * frame-major: frame i at dev_frames + i*pixels.  Go cannot pass [][]float32 through cgo, so frames
+ * are handed over one at a time (&f[i].Data[lower], a pointer-free slice). */
+int  nl_stack_begin(nl_ctx *ctx, int32_t n_frames, int64_t pixels, nl_stack_job **job);
+int  nl_stack_put_frame(nl_stack_job *job, int32_t i, const float *host, int64_t count);   /* H2D, async on the stream */
+int  nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_stride);   /* device-resident producers */
+/* Runs one stacking pass.  mode/sigma/ref_frame_loc are OpStack's fields (stack.go:66-73); weights is
+ * NULL (StWeightNone) or n_frames floats from nl_get_weights.  The result (pixels floats) and the two
+ * clip counters (stack.go:140, widened to 64 bit) go to host memory; blocks until they are there. */
+int  nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                  float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
+/* Same, result left in device memory (dev_out: pixels floats), asynchronous on the context's stream;
+ * the clip counters are readable after nl_ctx_sync via nl_stack_clip_counts. */
+int  nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                      float ref_frame_loc, float *dev_out);
+int  nl_stack_clip_counts(nl_stack_job *job, int64_t *clip_low, int64_t *clip_high);
+int  nl_stack_end(nl_stack_job *job);
+/* autoSelectStackingMode (stack.go:45-55) */
+int  nl_auto_select_mode(int32_t n_frames);
+/* getWeights (stack.go:231-270) on the per-frame scalars it reads (Exposure, Stats.Noise(), HFR). */
+int  nl_get_weights(int32_t weighting, const float *exposure, const float *noise, const float *hfr,
+                    int32_t n_frames, float *weights);
+
+/* ---- batches: replaces StackIncremental / StackIncrementalFinalize (stack.go:924-944) -------
+ * acc = light*weight (first != 0) or acc += light*weight; then acc *= 1/weight_sum.  Device buffers. */
+int  nl_stack_incremental_dev(nl_ctx *ctx, float *dev_acc, const float *dev_light, int64_t pixels, float weight, int first);
+int  nl_stack_incremental_finalize_dev(nl_ctx *ctx, float *dev_acc, int64_t pixels, float weight_sum);
+
+/* ---- resample: replaces (*Image).Project (internal/fits/project.go:26-76) ------------------
+ * trans = Transform2D{A..F} (internal/star/coord.go:52-59); inverted on the host exactly like
+ * Transform2D.Invert (coord.go:159-201); out_of_bounds = fill value (NaN for stacking). */
+int  nl_transform_invert(const float trans[6], float inv[6]);
+int  nl_project(nl_ctx *ctx, const float *host_src, int32_t src_w, int32_t src_h,
+                float *host_dst, int32_t dst_w, int32_t dst_h, const float trans[6], float out_of_bounds);
+int  nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t src_w, int32_t src_h,
+                    float *dev_dst, int32_t dst_w, int32_t dst_h, const float trans[6], float out_of_bounds);
+
+/* ---- star detection: replaces star.FindStars (internal/star/findstars.go:59-100) -----------
+ * nl_find_bright = findBrightPixels (findstars.go:105-129): candidates in raster order.  *count is
+ * the true number found; at most cap are stored. */
+int  nl_find_bright(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float threshold,
+                    int32_t radius, nl_star *out, int32_t cap, int32_t *count);
+int  nl_find_bright_dev(nl_ctx *ctx, const float *dev_data, int32_t len, int32_t width, float threshold,
+                        int32_t radius, nl_star *out, int32_t cap, int32_t *count);
+/* The whole FindStars pipeline.  median_diff_stddev stands for medianDiffStats.StdDev(); it must be
+ * given when bp_sigma > 0 (the reference's nil fallback draws a random sample, findstars.go:139-150). */
+int  nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float location, float scale,
+                   float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
+                   nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr);
+
+/* ---- synthetic frames (the workload generator, not reference code) --- */
+int  nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64_t count, uint32_t frame, uint32_t seed);
+
+/* ---- plain device memory helpers for bindings without a CUDA runtime of their own --------- */
+int  nl_dev_alloc(nl_ctx *ctx, int64_t bytes, void **dev);
+int  nl_dev_free(nl_ctx *ctx, void *dev);
+int  nl_host_alloc_pinned(int64_t bytes, void **host);
+int  nl_host_free_pinned(void *host);
+int  nl_memcpy_h2d(nl_ctx *ctx, void *dev, const void *host, int64_t bytes);   /* async on the stream */
+int  nl_memcpy_d2h(nl_ctx *ctx, void *host, const void *dev, int64_t bytes);   /* async on the stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

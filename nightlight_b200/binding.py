@@ -1,0 +1,250 @@
+"""ctypes binding of include/nightlight_cuda.h.  No torch, no numpy tricks: plain pointers and sizes."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libnightlight_cuda.so")
+
+ST_MEDIAN, ST_MEAN, ST_SIGMA, ST_WINSOR_SIGMA, ST_MAD_SIGMA, ST_LINEAR_FIT, ST_AUTO = range(7)
+W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR = range(4)
+
+NL_E_INVALID, NL_E_CUDA, NL_E_UNSUPPORTED, NL_E_SINGULAR, NL_E_NOMEM, NL_E_WEIGHTS = -1, -2, -3, -4, -5, -6
+
+
+class NightlightError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+class Star(C.Structure):
+    """star.Star, internal/star/findstars.go:30-37"""
+    _fields_ = [("index", C.c_int32), ("value", C.c_float), ("x", C.c_float), ("y", C.c_float),
+                ("mass", C.c_float), ("hfr", C.c_float)]
+
+
+STAR_DTYPE = np.dtype([("index", "<i4"), ("value", "<f4"), ("x", "<f4"), ("y", "<f4"), ("mass", "<f4"), ("hfr", "<f4")])
+
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+
+# every symbol include/nightlight_cuda.h declares: name -> (restype, argtypes)
+DECLARED_SYMBOLS = {
+    "nl_last_error": (C.c_char_p, []),
+    "nl_version": (C.c_int, []),
+    "nl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "nl_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "nl_ctx_destroy": (C.c_int, [_vp]),
+    "nl_ctx_sync": (C.c_int, [_vp]),
+    "nl_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "nl_ctx_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "nl_ctx_launch_count": (C.c_int, [_vp, _i64p]),
+    "nl_stack_begin": (C.c_int, [_vp, C.c_int32, C.c_int64, C.POINTER(_vp)]),
+    "nl_stack_put_frame": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
+    "nl_stack_frames_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
+    "nl_stack_run": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp, _i64p, _i64p]),
+    "nl_stack_run_dev": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp]),
+    "nl_stack_clip_counts": (C.c_int, [_vp, _i64p, _i64p]),
+    "nl_stack_end": (C.c_int, [_vp]),
+    "nl_auto_select_mode": (C.c_int, [C.c_int32]),
+    "nl_get_weights": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, _fp]),
+    "nl_stack_incremental_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_int]),
+    "nl_stack_incremental_finalize_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_float]),
+    "nl_transform_invert": (C.c_int, [_fp, _fp]),
+    "nl_project": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float]),
+    "nl_project_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float]),
+    "nl_find_bright": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, C.c_int32, _i32p]),
+    "nl_find_bright_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, C.c_int32, _i32p]),
+    "nl_find_stars": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_int32, C.c_float, _vp, C.c_int32, _i32p, _fp, _fp]),
+    "nl_synth_fill_dev": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32]),
+    "nl_dev_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
+    "nl_dev_free": (C.c_int, [_vp, _vp]),
+    "nl_host_alloc_pinned": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
+    "nl_host_free_pinned": (C.c_int, [_vp]),
+    "nl_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    "nl_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _SO
+
+
+def load_library():
+    """Loads libnightlight_cuda.so.  Fails loudly when it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise NightlightError(NL_E_CUDA, "libnightlight_cuda.so is missing (%s): build it with "
+                                  "`make -C nightlight_b200/csrc` or __graft_entry__.build(); there is no CPU fallback" % _SO)
+        lib = C.CDLL(_SO)
+        for name, (res, args) in DECLARED_SYMBOLS.items():
+            fn = getattr(lib, name)     # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().nl_last_error()
+        raise NightlightError(rc, (msg or b"").decode("utf-8", "replace") or "nightlight_cuda error %d" % rc)
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+class Context:
+    """One CUDA device + one stream (nl_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = _vp()
+        check(load_library().nl_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            load_library().nl_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        check(load_library().nl_ctx_sync(self._h))
+
+    @property
+    def stream(self):
+        s = _vp()
+        check(load_library().nl_ctx_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def launch_count(self):
+        n = C.c_int64()
+        check(load_library().nl_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # raw device memory (bench / tests)
+    def dev_alloc(self, nbytes):
+        p = _vp()
+        check(load_library().nl_dev_alloc(self._h, int(nbytes), C.byref(p)))
+        return p.value
+
+    def dev_free(self, ptr):
+        check(load_library().nl_dev_free(self._h, _vp(ptr)))
+
+    def h2d(self, dev, host_array):
+        a = np.ascontiguousarray(host_array)
+        check(load_library().nl_memcpy_h2d(self._h, _vp(dev), a.ctypes.data_as(_vp), a.nbytes))
+        self.sync()
+
+    def d2h(self, host_array, dev):
+        assert host_array.flags["C_CONTIGUOUS"]
+        check(load_library().nl_memcpy_d2h(self._h, host_array.ctypes.data_as(_vp), _vp(dev), host_array.nbytes))
+        self.sync()
+
+    def synth_fill(self, dev, p0, count, frame, seed=12345):
+        check(load_library().nl_synth_fill_dev(self._h, _vp(dev), int(p0), int(count), int(frame), int(seed)))
+
+
+class StackJob:
+    """nl_stack_job: N frames (or one row stripe of them) resident in device memory, frame-major."""
+
+    def __init__(self, ctx, n_frames, pixels):
+        self.ctx, self.n_frames, self.pixels = ctx, int(n_frames), int(pixels)
+        self._h = _vp()
+        check(load_library().nl_stack_begin(ctx.handle, self.n_frames, self.pixels, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            load_library().nl_stack_end(self._h)
+            self._h = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def put_frame(self, i, host):
+        """host: float32 array of `pixels` samples, or a raw (pointer, count) pair."""
+        if isinstance(host, tuple):
+            ptr, count = host
+            check(load_library().nl_stack_put_frame(self._h, int(i), _vp(ptr), int(count)))
+            return
+        # pageable memory is staged by the CUDA runtime before the call returns; a pinned buffer must
+        # stay valid until the next sync
+        a = _f32(host).reshape(-1)
+        check(load_library().nl_stack_put_frame(self._h, int(i), a.ctypes.data_as(_vp), a.size))
+
+    @property
+    def frames_dev(self):
+        p, stride = _vp(), C.c_int64()
+        check(load_library().nl_stack_frames_dev(self._h, C.byref(p), C.byref(stride)))
+        return p.value, stride.value
+
+    def synth_fill(self, p0=0, seed=12345):
+        base, stride = self.frames_dev
+        for k in range(self.n_frames):
+            self.ctx.synth_fill(base + 4 * k * stride, p0, self.pixels, k, seed)
+
+    @staticmethod
+    def _weights(weights, n):
+        if weights is None:
+            return None, None
+        w = _f32(weights).reshape(-1)
+        if w.size != n:
+            raise NightlightError(NL_E_INVALID, "weights must have one entry per frame")
+        return w, w.ctypes.data_as(_fp)
+
+    def run(self, mode, weights=None, sigma_low=2.75, sigma_high=2.75, ref_frame_loc=0.0, out=None):
+        """-> (result float32[pixels], clipLow, clipHigh); blocks until the result is on the host."""
+        w, wp = self._weights(weights, self.n_frames)
+        if out is None:
+            out = np.empty(self.pixels, dtype=np.float32)
+        cl, ch = C.c_int64(), C.c_int64()
+        check(load_library().nl_stack_run(self._h, int(mode), wp, sigma_low, sigma_high, ref_frame_loc,
+                                          out.ctypes.data_as(_vp), C.byref(cl), C.byref(ch)))
+        return out, cl.value, ch.value
+
+    def run_dev(self, mode, dev_out, weights=None, sigma_low=2.75, sigma_high=2.75, ref_frame_loc=0.0):
+        """asynchronous; result stays in device memory at dev_out"""
+        w, wp = self._weights(weights, self.n_frames)
+        check(load_library().nl_stack_run_dev(self._h, int(mode), wp, sigma_low, sigma_high, ref_frame_loc, _vp(dev_out)))
+        if w is not None:
+            self.ctx.sync()
+
+    def clip_counts(self):
+        cl, ch = C.c_int64(), C.c_int64()
+        check(load_library().nl_stack_clip_counts(self._h, C.byref(cl), C.byref(ch)))
+        return cl.value, ch.value

@@ -1,0 +1,162 @@
+// nl_api.cu -- context, error reporting and memory helpers of libnightlight_cuda.so.
+// The reference is one Go process with goroutines; the one boundary this
+// library adds is Go <-> C ABI <-> CUDA.  A context = one device + one stream.
+#include "nl_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace nl {
+
+static thread_local std::string g_last_error;
+
+int set_error(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    return set_error(NL_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int ensure_scratch(nl_ctx *ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return NL_OK;
+    if (ctx->scratch) {
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+        NL_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    NL_CUDA(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return NL_OK;
+}
+
+}  // namespace nl
+
+using namespace nl;
+
+extern "C" {
+
+const char *nl_last_error(void) { return g_last_error.c_str(); }
+
+int nl_version(void) { return 100; }   // 0.1.0
+
+int nl_device_count(int *count) {
+    NL_REQUIRE(count, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    return NL_OK;
+}
+
+int nl_ctx_create(int device, nl_ctx **out) {
+    NL_REQUIRE(out, "ctx out pointer is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_error(NL_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return set_error(NL_E_INVALID, "device %d out of range [0,%d)", device, count);
+    NL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_error(NL_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                         prop.major, prop.minor);
+    nl_ctx *c = new nl_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    *out = c;
+    return NL_OK;
+}
+
+int nl_ctx_destroy(nl_ctx *ctx) {
+    if (!ctx) return NL_OK;
+    CtxGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return NL_OK;
+}
+
+int nl_ctx_sync(nl_ctx *ctx) {
+    NL_REQUIRE(ctx, "ctx is NULL");
+    CtxGuard g(ctx);
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NL_OK;
+}
+
+int nl_ctx_stream(nl_ctx *ctx, void **stream) {
+    NL_REQUIRE(ctx && stream, "NULL argument");
+    *stream = (void *)ctx->stream;
+    return NL_OK;
+}
+
+int nl_ctx_device(nl_ctx *ctx, int *device) {
+    NL_REQUIRE(ctx && device, "NULL argument");
+    *device = ctx->device;
+    return NL_OK;
+}
+
+int nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches) {
+    NL_REQUIRE(ctx && launches, "NULL argument");
+    *launches = ctx->launches.load();
+    return NL_OK;
+}
+
+int nl_dev_alloc(nl_ctx *ctx, int64_t bytes, void **dev) {
+    NL_REQUIRE(ctx && dev && bytes >= 0, "bad argument");
+    CtxGuard g(ctx);
+    cudaError_t e = cudaMalloc(dev, (size_t)(bytes > 0 ? bytes : 1));
+    if (e == cudaErrorMemoryAllocation) return set_error(NL_E_NOMEM, "cudaMalloc of %lld bytes failed", (long long)bytes);
+    NL_CUDA(e);
+    return NL_OK;
+}
+
+int nl_dev_free(nl_ctx *ctx, void *dev) {
+    NL_REQUIRE(ctx, "ctx is NULL");
+    CtxGuard g(ctx);
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    NL_CUDA(cudaFree(dev));
+    return NL_OK;
+}
+
+int nl_host_alloc_pinned(int64_t bytes, void **host) {
+    NL_REQUIRE(host && bytes >= 0, "bad argument");
+    cudaError_t e = cudaHostAlloc(host, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocPortable);
+    if (e == cudaErrorMemoryAllocation) return set_error(NL_E_NOMEM, "cudaHostAlloc of %lld bytes failed", (long long)bytes);
+    NL_CUDA(e);
+    return NL_OK;
+}
+
+int nl_host_free_pinned(void *host) {
+    NL_CUDA(cudaFreeHost(host));
+    return NL_OK;
+}
+
+int nl_memcpy_h2d(nl_ctx *ctx, void *dev, const void *host, int64_t bytes) {
+    NL_REQUIRE(ctx && bytes >= 0, "bad argument");
+    CtxGuard g(ctx);
+    NL_CUDA(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NL_OK;
+}
+
+int nl_memcpy_d2h(nl_ctx *ctx, void *host, const void *dev, int64_t bytes) {
+    NL_REQUIRE(ctx && bytes >= 0, "bad argument");
+    CtxGuard g(ctx);
+    NL_CUDA(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return NL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// nl_internal.h -- shared declarations of libnightlight_cuda.so (not installed; the public
+// interface is include/nightlight_cuda.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/nightlight_cuda.h"
+
+struct nl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int max_smem_optin = 0;          // bytes of dynamic shared memory one CTA may opt in to
+    int smem_per_sm = 0;
+    std::atomic<int64_t> launches{0};
+    // scratch owned by the context, grown on demand (star scan)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace nl {
+
+int set_error(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+int ensure_scratch(nl_ctx *ctx, size_t bytes);
+
+#define NL_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return nl::cuda_fail(e__, #call); \
+    } while (0)
+
+#define NL_REQUIRE(cond, msg)                                \
+    do {                                                     \
+        if (!(cond)) return nl::set_error(NL_E_INVALID, "%s", msg); \
+    } while (0)
+
+struct CtxGuard {   // make the context's device current for the calling thread
+    int prev = -1;
+    bool ok = true;
+    explicit CtxGuard(const nl_ctx *c) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != c->device) ok = cudaSetDevice(c->device) == cudaSuccess;
+    }
+    ~CtxGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace nl

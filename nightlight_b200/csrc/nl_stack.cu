@@ -1,0 +1,438 @@
+// nl_stack.cu -- the stacking kernels and the job API (nl_stack_*).
+//
+// Replaces OpStack.Apply and the nine Stack* reducers of the reference
+// (internal/ops/stack/stack.go:115-227, 274-918).  Data layout in HBM: one job buffer
+// [n_frames][pixels] fp32, frame-major, so the column of pixel p is a stride-`pixels` gather and the
+// 32 lanes of a warp read 128 contiguous bytes of each frame.
+//
+// Kernel families
+//   stack_mean_kernel    StackMean / StackMeanWeighted: pure streaming, sequential sum in frame
+//                        order per pixel, float4 (4 pixels per thread), no shared memory.
+//   stack_column_kernel  every order-statistics mode: a warp owns a tile of S pixels (S = 32:
+//                        lane == pixel == shared-memory bank), gathers the non-NaN samples of its
+//                        pixels into shared memory [sample][lane], then every lane reduces its own
+//                        column with the routines of nl_column.cuh, which reproduce the reference's
+//                        quick-select permutation and fp32 evaluation order exactly.
+// Persistent grid: warps stride over tiles; warps of one SM are in different phases (loading /
+// reducing), which overlaps the HBM stream with the latency-bound column work.
+#include "nl_internal.h"
+#include "nl_column.cuh"
+
+#include <vector>
+
+namespace nl {
+
+struct StackArgs {
+    const float *frames;     // [n][stride]
+    long long stride;        // elements between frames
+    long long pixels;
+    int n;
+    const float *weights;    // [n] or nullptr
+    const float *ramp;       // [2*(n+1)] MeanStdDev of 0..c-1, linear fit only
+    float ref_loc, sig_lo, sig_hi;
+    float *out;              // [pixels]
+    unsigned long long *clip;   // [2] low, high
+};
+
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+
+// ---- StackMean / StackMeanWeighted (stack.go:307-366) ----------------------------------------
+template <bool W, int V>   // V pixels per thread (4: float4 path, 1: scalar path)
+__global__ void __launch_bounds__(256) stack_mean_kernel(StackArgs a) {
+    long long groups = (a.pixels + V - 1) / V;
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < groups;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        long long p = gidx * V;
+        float sum[V], wsum[V];
+        int num[V];
+#pragma unroll
+        for (int c = 0; c < V; c++) { sum[c] = 0.0f; wsum[c] = 0.0f; num[c] = 0; }
+        const float *src = a.frames + p;
+#pragma unroll 8
+        for (int k = 0; k < a.n; k++) {
+            float v[V];
+            if (V == 4) {
+                float4 q = __ldcs(reinterpret_cast<const float4 *>(src + (long long)k * a.stride));
+                v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w;
+            } else {
+                v[0] = __ldcs(src + (long long)k * a.stride);
+            }
+            float w = W ? __ldg(a.weights + k) : 1.0f;
+#pragma unroll
+            for (int c = 0; c < V; c++) {
+                if (v[c] == v[c]) {
+                    if (W) { sum[c] = __fadd_rn(sum[c], __fmul_rn(v[c], w)); wsum[c] = __fadd_rn(wsum[c], w); }
+                    else sum[c] = __fadd_rn(sum[c], v[c]);
+                    num[c]++;
+                }
+            }
+        }
+        float r[V];
+#pragma unroll
+        for (int c = 0; c < V; c++)
+            r[c] = num[c] == 0 ? a.ref_loc : __fdiv_rn(sum[c], W ? wsum[c] : (float)num[c]);
+        if (V == 4) *reinterpret_cast<float4 *>(a.out + p) = make_float4(r[0], r[1 % V], r[2 % V], r[3 % V]);
+        else a.out[p] = r[0];
+    }
+}
+
+// ---- order-statistics modes ------------------------------------------------------------------
+template <int MODE, bool W> struct ColumnBufs {           // shared-memory columns per pixel
+    static constexpr int value = 1 + (W ? 1 : 0) + ((MODE == ST_WINSOR || MODE == ST_MAD) ? 1 : 0);
+};
+
+template <int MODE, bool W, int S>
+__global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int n = a.n;
+    constexpr int NB = ColumnBufs<MODE, W>::value;
+    float *g = smem + (size_t)warp * NB * S * n + lane;          // column element i at g[i*S]
+    float *gw = W ? g + (size_t)S * n : nullptr;
+    float *sc = g + (size_t)(W ? 2 : 1) * S * n;                  // winsor / MAD scratch
+    (void)sc;
+
+    const long long tiles = (a.pixels + S - 1) / S;
+    const long long warp_gid = (long long)blockIdx.x * warps_per_cta + warp;
+    const long long warp_cnt = (long long)gridDim.x * warps_per_cta;
+    int ncl = 0, nch = 0;
+
+    for (long long t = warp_gid; t < tiles; t += warp_cnt) {
+        const long long p = t * S + lane;
+        const bool active = lane < S && p < a.pixels;
+        if (active) {
+            // gather the non-NaN samples of pixel p in frame order (stack.go:380-387)
+            const float *src = a.frames + p;
+            int cur = 0;
+            int k = 0;
+            for (; k + 8 <= n; k += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = ld_stream(src + (long long)(k + u) * a.stride);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    g[cur * S] = v[u];
+                    if (W) gw[cur * S] = __ldg(a.weights + k + u);
+                    cur += (v[u] == v[u]) ? 1 : 0;
+                }
+            }
+            for (; k < n; k++) {
+                float v = ld_stream(src + (long long)k * a.stride);
+                if (v == v) {
+                    g[cur * S] = v;
+                    if (W) gw[cur * S] = __ldg(a.weights + k);
+                    cur++;
+                }
+            }
+            float res;
+            if (cur == 0) {
+                res = a.ref_loc;                                   // stack.go:388-397
+            } else if (MODE == ST_MEDIAN) {
+                res = qselect_median<S>(g, cur);                   // stack.go:274-303
+            } else if (MODE == ST_SIGMA) {
+                res = reduce_sigma<S, W>(g, gw, cur, a.sig_lo, a.sig_hi, ncl, nch);
+            } else if (MODE == ST_WINSOR) {
+                res = reduce_winsor<S, W>(g, gw, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+            } else if (MODE == ST_MAD) {
+                res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+            } else {
+                res = reduce_linfit<S>(g, cur, a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
+            }
+            a.out[p] = res;
+        }
+        __syncwarp();
+    }
+    if (MODE >= ST_SIGMA) {
+        // clip totals (stack.go:193-198): warp reduce, one atomic pair per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ncl += __shfl_xor_sync(0xffffffffu, ncl, o);
+            nch += __shfl_xor_sync(0xffffffffu, nch, o);
+        }
+        if (lane == 0 && (ncl | nch)) {
+            atomicAdd(a.clip + 0, (unsigned long long)ncl);
+            atomicAdd(a.clip + 1, (unsigned long long)nch);
+        }
+    }
+}
+
+__global__ void ramp_kernel(float *ramp, int n) {
+    // ramp[2c], ramp[2c+1] = MeanStdDev(0..c-1), exactly as the reference computes it per pixel
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= n; c += gridDim.x * blockDim.x) {
+        float m = 0.0f, s = 0.0f;
+        if (c > 0) ramp_mean_stddev(c, m, s);
+        ramp[2 * c] = m;
+        ramp[2 * c + 1] = s;
+    }
+}
+
+}  // namespace nl
+
+using namespace nl;
+
+struct nl_stack_job {
+    nl_ctx *ctx = nullptr;
+    int n = 0;
+    long long pixels = 0;
+    float *frames = nullptr;          // [n][pixels]
+    float *out = nullptr;             // [pixels], used by nl_stack_run
+    float *weights = nullptr;         // [n]
+    float *ramp = nullptr;            // [2*(n+1)]
+    bool ramp_ready = false;
+    unsigned long long *clip = nullptr;   // [2] device
+    unsigned long long *clip_host = nullptr;   // [2] pinned
+};
+
+namespace nl {
+
+template <int MODE, bool W, int S>
+static int launch_column(nl_stack_job *job, const StackArgs &args) {
+    nl_ctx *ctx = job->ctx;
+    constexpr int NB = ColumnBufs<MODE, W>::value;
+    const size_t per_warp = (size_t)NB * S * job->n * sizeof(float);
+    const size_t cap = (size_t)ctx->max_smem_optin;
+    if (per_warp > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
+    int warps = (int)(cap / per_warp);
+    if (warps > 8) warps = 8;
+    const size_t smem = per_warp * warps;
+    auto kern = stack_column_kernel<MODE, W, S>;
+    NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 0;
+    NL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const long long tiles = (job->pixels + S - 1) / S;
+    long long grid = (long long)ctx->sm_count * ctas_per_sm;
+    const long long need = (tiles + warps - 1) / warps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(args);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}
+
+template <int MODE, bool W>
+static int launch_column_s(nl_stack_job *job, const StackArgs &args) {
+    constexpr int NB = ColumnBufs<MODE, W>::value;
+    const size_t per_pixel = (size_t)NB * job->n * sizeof(float);
+    const size_t cap = (size_t)job->ctx->max_smem_optin;
+    if (per_pixel * 32 <= cap) return launch_column<MODE, W, 32>(job, args);
+    if (per_pixel * 8 <= cap) return launch_column<MODE, W, 8>(job, args);
+    return launch_column<MODE, W, 1>(job, args);
+}
+
+template <bool W>
+static int launch_mean(nl_stack_job *job, const StackArgs &args) {
+    nl_ctx *ctx = job->ctx;
+    const bool vec = (job->pixels % 4) == 0;
+    const long long groups = vec ? job->pixels / 4 : job->pixels;
+    long long grid = (groups + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if (vec) stack_mean_kernel<W, 4><<<(unsigned)grid, 256, 0, ctx->stream>>>(args);
+    else stack_mean_kernel<W, 1><<<(unsigned)grid, 256, 0, ctx->stream>>>(args);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}
+
+static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, float sig_lo, float sig_hi,
+                        float ref_loc, float *dev_out) {
+    nl_ctx *ctx = job->ctx;
+    if (mode < NL_ST_MEDIAN || mode > NL_ST_AUTO) return set_error(NL_E_INVALID, "invalid stacking mode");   // stack.go:118-120
+    if (mode == NL_ST_AUTO) mode = auto_select_mode(job->n);
+    const bool weighted = host_weights != nullptr;
+    if (mode == NL_ST_MAD_SIGMA && weighted)
+        return set_error(NL_E_UNSUPPORTED, "MADSigma stacking with weights is still unimplemented");         // stack.go:185
+    NL_CUDA(cudaMemsetAsync(job->clip, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (job->pixels == 0) return NL_OK;
+    if (weighted)
+        NL_CUDA(cudaMemcpyAsync(job->weights, host_weights, sizeof(float) * job->n, cudaMemcpyHostToDevice, ctx->stream));
+    if (mode == NL_ST_LINEAR_FIT && !job->ramp_ready) {
+        ramp_kernel<<<(job->n + 128) / 128, 128, 0, ctx->stream>>>(job->ramp, job->n);
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        job->ramp_ready = true;
+    }
+    StackArgs a;
+    a.frames = job->frames; a.stride = job->pixels; a.pixels = job->pixels; a.n = job->n;
+    a.weights = weighted ? job->weights : nullptr; a.ramp = job->ramp;
+    a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip;
+    switch (mode) {
+    case NL_ST_MEDIAN: return launch_column_s<ST_MEDIAN, false>(job, a);     // weights ignored, stack.go:160-161
+    case NL_ST_MEAN: return weighted ? launch_mean<true>(job, a) : launch_mean<false>(job, a);
+    case NL_ST_SIGMA: return weighted ? launch_column_s<ST_SIGMA, true>(job, a) : launch_column_s<ST_SIGMA, false>(job, a);
+    case NL_ST_WINSOR_SIGMA: return weighted ? launch_column_s<ST_WINSOR, true>(job, a) : launch_column_s<ST_WINSOR, false>(job, a);
+    case NL_ST_MAD_SIGMA: return launch_column_s<ST_MAD, false>(job, a);
+    case NL_ST_LINEAR_FIT: return launch_column_s<ST_LINFIT, false>(job, a);   // weights ignored, stack.go:188-189
+    }
+    return set_error(NL_E_INVALID, "invalid stacking mode");
+}
+
+}  // namespace nl
+
+extern "C" {
+
+int nl_auto_select_mode(int32_t n_frames) { return auto_select_mode(n_frames); }
+
+// getWeights, stack.go:231-270
+int nl_get_weights(int32_t weighting, const float *exposure, const float *noise, const float *hfr, int32_t n,
+                   float *weights) {
+    NL_REQUIRE(n >= 0, "n_frames < 0");
+    if (weighting == NL_W_NONE) return NL_OK;
+    NL_REQUIRE(weights, "weights is NULL");
+    if (weighting == NL_W_EXPOSURE) {
+        NL_REQUIRE(exposure, "exposure is NULL");
+        for (int i = 0; i < n; i++) {
+            if (exposure[i] == 0) return set_error(NL_E_WEIGHTS, "Missing exposure information for exposure-weighted stacking");
+            weights[i] = exposure[i];
+        }
+        return NL_OK;
+    }
+    if (weighting == NL_W_INVERSE_NOISE || weighting == NL_W_INVERSE_HFR) {
+        const float *x = weighting == NL_W_INVERSE_NOISE ? noise : hfr;
+        NL_REQUIRE(x, "noise / hfr is NULL");
+        float mn = 3.40282346638528859811704183484516925440e+38f, mx = -mn;
+        for (int i = 0; i < n; i++) {
+            if (x[i] < mn) mn = x[i];
+            if (x[i] > mx) mx = x[i];
+        }
+        for (int i = 0; i < n; i++) weights[i] = 1.0f / (1.0f + 4.0f * (x[i] - mn) / (mx - mn));
+        return NL_OK;
+    }
+    return set_error(NL_E_WEIGHTS, "invalid weighting mode %d", weighting);
+}
+
+int nl_stack_begin(nl_ctx *ctx, int32_t n_frames, int64_t pixels, nl_stack_job **out) {
+    NL_REQUIRE(ctx && out, "NULL argument");
+    *out = nullptr;
+    NL_REQUIRE(n_frames >= 1, "n_frames must be >= 1");
+    NL_REQUIRE(pixels >= 0, "pixels must be >= 0");
+    CtxGuard g(ctx);
+    nl_stack_job *j = new nl_stack_job();
+    j->ctx = ctx; j->n = n_frames; j->pixels = pixels;
+    size_t frame_bytes = sizeof(float) * (size_t)n_frames * (size_t)(pixels > 0 ? pixels : 1);
+    cudaError_t e = cudaMalloc(&j->frames, frame_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&j->out, sizeof(float) * (size_t)(pixels > 0 ? pixels : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&j->weights, sizeof(float) * (size_t)n_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&j->ramp, sizeof(float) * 2 * ((size_t)n_frames + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&j->clip, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc(&j->clip_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        nl_stack_end(j);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            return set_error(NL_E_NOMEM, "out of device memory for %d frames x %lld pixels", n_frames, (long long)pixels);
+        }
+        return cuda_fail(e, "nl_stack_begin allocation");
+    }
+    j->clip_host[0] = j->clip_host[1] = 0;
+    *out = j;
+    return NL_OK;
+}
+
+int nl_stack_put_frame(nl_stack_job *job, int32_t i, const float *host, int64_t count) {
+    NL_REQUIRE(job && host, "NULL argument");
+    NL_REQUIRE(i >= 0 && i < job->n, "frame index out of range");
+    NL_REQUIRE(count == job->pixels, "frame size differs from the job's pixel count");
+    CtxGuard g(job->ctx);
+    NL_CUDA(cudaMemcpyAsync(job->frames + (size_t)i * job->pixels, host, sizeof(float) * (size_t)count,
+                            cudaMemcpyHostToDevice, job->ctx->stream));
+    return NL_OK;
+}
+
+int nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_stride) {
+    NL_REQUIRE(job && dev_frames, "NULL argument");
+    *dev_frames = job->frames;
+    if (frame_stride) *frame_stride = job->pixels;
+    return NL_OK;
+}
+
+int nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                     float ref_frame_loc, float *dev_out) {
+    NL_REQUIRE(job && (dev_out || job->pixels == 0), "NULL argument");
+    CtxGuard g(job->ctx);
+    int rc = stack_launch(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, dev_out);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(job->clip_host, job->clip, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            job->ctx->stream));
+    return NL_OK;
+}
+
+int nl_stack_clip_counts(nl_stack_job *job, int64_t *clip_low, int64_t *clip_high) {
+    NL_REQUIRE(job, "NULL argument");
+    if (clip_low) *clip_low = (int64_t)job->clip_host[0];
+    if (clip_high) *clip_high = (int64_t)job->clip_host[1];
+    return NL_OK;
+}
+
+int nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                 float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
+    NL_REQUIRE(job && (host_out || job->pixels == 0), "NULL argument");
+    CtxGuard g(job->ctx);
+    int rc = nl_stack_run_dev(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, job->out);
+    if (rc != NL_OK) return rc;
+    if (job->pixels > 0)
+        NL_CUDA(cudaMemcpyAsync(host_out, job->out, sizeof(float) * (size_t)job->pixels, cudaMemcpyDeviceToHost,
+                                job->ctx->stream));
+    NL_CUDA(cudaStreamSynchronize(job->ctx->stream));
+    return nl_stack_clip_counts(job, clip_low, clip_high);
+}
+
+int nl_stack_end(nl_stack_job *job) {
+    if (!job) return NL_OK;
+    CtxGuard g(job->ctx);
+    cudaStreamSynchronize(job->ctx->stream);
+    if (job->frames) cudaFree(job->frames);
+    if (job->out) cudaFree(job->out);
+    if (job->weights) cudaFree(job->weights);
+    if (job->ramp) cudaFree(job->ramp);
+    if (job->clip) cudaFree(job->clip);
+    if (job->clip_host) cudaFreeHost(job->clip_host);
+    delete job;
+    return NL_OK;
+}
+
+// StackIncremental / StackIncrementalFinalize, stack.go:924-944
+__global__ void incremental_kernel(float *acc, const float *light, long long n, float w, int first) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float t = __fmul_rn(light[i], w);
+        acc[i] = first ? t : __fadd_rn(acc[i], t);
+    }
+}
+__global__ void scale_kernel(float *acc, long long n, float factor) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc[i] = __fmul_rn(acc[i], factor);
+}
+
+int nl_stack_incremental_dev(nl_ctx *ctx, float *dev_acc, const float *dev_light, int64_t pixels, float weight, int first) {
+    NL_REQUIRE(ctx && pixels >= 0, "bad argument");
+    if (pixels == 0) return NL_OK;
+    NL_REQUIRE(dev_acc && dev_light, "NULL argument");
+    CtxGuard g(ctx);
+    long long grid = (pixels + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
+    incremental_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, dev_light, pixels, weight, first);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}
+
+int nl_stack_incremental_finalize_dev(nl_ctx *ctx, float *dev_acc, int64_t pixels, float weight_sum) {
+    NL_REQUIRE(ctx && pixels >= 0, "bad argument");
+    if (pixels == 0) return NL_OK;
+    NL_REQUIRE(dev_acc, "NULL argument");
+    CtxGuard g(ctx);
+    float factor = 1.0f / weight_sum;    // stack.go:941
+    long long grid = (pixels + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
+    scale_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, pixels, factor);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// nl_stars.cu -- star detection: the full-frame threshold scan on the GPU, the sparse per-star
+// steps on the host.  Replaces star.FindStars (internal/star/findstars.go:59-100).
+//
+// The reference's detector is not a convolution: it is a raster scan for pixels above
+// location + scale*starSig with a sequential same-row de-duplication against the last kept
+// candidate (findstars.go:105-129), followed by sparse per-star work (3x3 median reject, unstable
+// quicksort by mass, grid overlap filter, iterative centre of mass, half-flux radius).  Only the
+// scan touches every pixel (4 B/pixel, HBM bound); it is the part that runs on the device:
+//
+//   bright_rows_kernel<false>  one warp per image row streams the row (coalesced 128 B per load,
+//                              8 loads in flight per lane), ballots the hits and replays the
+//                              reference's de-duplication state machine over the hit bits in raster
+//                              order -- the dependency never crosses a row, because a candidate
+//                              only merges with a predecessor of the same Y.  Emits the row's count.
+//   row_offsets_kernel         exclusive prefix sum of the row counts (raster order of the output).
+//   bright_rows_kernel<true>   the same walk again, now writing each row's candidates at its offset
+//                              (the second read of the frame is served largely by the 126 MB L2).
+#include "nl_internal.h"
+
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+namespace nl {
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) bright_rows_kernel(const float *__restrict__ data, int len, int width, int rows,
+                                                          float threshold, int radius, int *__restrict__ row_count,
+                                                          const int *__restrict__ row_offset, nl_star *__restrict__ out,
+                                                          int cap) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (row >= rows) return;
+    const long long row0 = (long long)row * width;
+    const int row_len = (int)min((long long)width, (long long)len - row0);
+    const float *src = data + row0;
+    const int base_out = WRITE ? row_offset[row] : 0;
+
+    int count = 0;            // candidates kept in this row so far (warp-uniform)
+    int last_x = 0;           // the last kept candidate of this row
+    float last_v = 0.0f;
+    constexpr int U = 8;
+    for (int x0 = 0; x0 < row_len; x0 += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int x = x0 + u * 32 + lane;
+            v[u] = x < row_len ? __ldcs(src + x) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int x = x0 + u * 32 + lane;
+            unsigned hits = __ballot_sync(0xffffffffu, x < row_len && v[u] > threshold);
+            while (hits) {                                   // raster order within the chunk
+                const int b = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float hv = __shfl_sync(0xffffffffu, v[u], b);
+                const int hx = x0 + u * 32 + b;
+                // findstars.go:113-123: same row and within `radius` of the last kept candidate
+                if (count > 0 && last_x >= hx - radius) {
+                    if (last_v >= hv) continue;              // keep the older, brighter one
+                } else {
+                    count++;
+                }
+                last_x = hx; last_v = hv;
+                if (WRITE && lane == 0) {
+                    const long long slot = (long long)base_out + count - 1;
+                    if (slot < cap) {
+                        nl_star s;
+                        s.index = (int)(row0 + hx); s.value = hv; s.x = (float)hx; s.y = (float)row;
+                        s.mass = hv; s.hfr = 1.0f;
+                        out[slot] = s;
+                    }
+                }
+            }
+        }
+    }
+    if (!WRITE && lane == 0) row_count[row] = count;
+}
+
+// exclusive scan of the row counts; rows <= a few 10^4, one CTA is plenty
+__global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict__ row_count, int *__restrict__ row_offset,
+                                                           int rows, int *__restrict__ total) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < rows; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = i < rows ? row_count[i] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;     // exclusive
+        }
+        __syncthreads();
+        const int excl = carry + warp_sums[warp] + incl - c;
+        if (i < rows) row_offset[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// pass 1: per-row counts and offsets; *count = number of candidates in the frame
+static int bright_count(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius, int *count) {
+    *count = 0;
+    if (len == 0) return NL_OK;
+    const int rows = (len + width - 1) / width;
+    // scratch: row_count[rows], row_offset[rows], total
+    const size_t ints = (size_t)2 * rows + 1;
+    int rc = ensure_scratch(ctx, (ints * sizeof(int) + 255) & ~(size_t)255);
+    if (rc != NL_OK) return rc;
+    int *row_count = (int *)ctx->scratch, *row_offset = row_count + rows, *total = row_offset + rows;
+    const int threads = 256, warps_per_cta = threads / 32;
+    const unsigned grid = (unsigned)((rows + warps_per_cta - 1) / warps_per_cta);
+    bright_rows_kernel<false><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
+                                                                nullptr, nullptr, 0);
+    NL_CUDA(cudaGetLastError());
+    row_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(row_count, row_offset, rows, total);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    NL_CUDA(cudaMemcpyAsync(count, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NL_OK;
+}
+
+// pass 2 (after bright_count on the same frame): write the first `keep` candidates in raster order
+static int bright_write(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius,
+                        nl_star *host_out, int keep) {
+    if (keep <= 0 || len == 0) return NL_OK;
+    const int rows = (len + width - 1) / width;
+    int *row_count = (int *)ctx->scratch, *row_offset = row_count + rows;
+    const int threads = 256, warps_per_cta = threads / 32;
+    const unsigned grid = (unsigned)((rows + warps_per_cta - 1) / warps_per_cta);
+    // the list lives in its own allocation so the offsets in the context scratch stay valid
+    nl_star *dev_list = nullptr;
+    NL_CUDA(cudaMalloc(&dev_list, sizeof(nl_star) * (size_t)keep));
+    bright_rows_kernel<true><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
+                                                               row_offset, dev_list, keep);
+    cudaError_t e = cudaGetLastError();
+    ctx->launches++;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host_out, dev_list, sizeof(nl_star) * (size_t)keep, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev_list);
+    if (e != cudaSuccess) return cuda_fail(e, "bright pixel scan");
+    return NL_OK;
+}
+
+static int find_bright_dev(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius,
+                           nl_star *host_out, int cap, int *count) {
+    int rc = bright_count(ctx, dev_data, len, width, threshold, radius, count);
+    if (rc != NL_OK) return rc;
+    return bright_write(ctx, dev_data, len, width, threshold, radius, host_out, *count < cap ? *count : cap);
+}
+
+// ---- sparse per-star steps on the host -------------------------------------------------------
+
+// CreateMask, findstars.go:187-200
+static std::vector<int32_t> create_mask(int32_t width, float radius) {
+    std::vector<int32_t> mask;
+    const int32_t rad = (int32_t)radius;
+    for (int32_t y = -rad; y <= rad; y++)
+        for (int32_t x = -rad; x <= rad; x++) {
+            const float dist = (float)sqrt((double)(y * y + x * x));
+            if (dist <= radius + 1e-8f) mask.push_back(y * width + x);
+        }
+    return mask;
+}
+
+static inline void cswap(float &a, float &b) { if (a > b) { float t = a; a = b; b = t; } }
+
+// MedianFloat32Slice9, median3x3.go:85-110 (the partially sorted buffer is an observable side effect)
+static float median9(float *a) {
+    cswap(a[0], a[1]); cswap(a[3], a[4]); cswap(a[6], a[7]);
+    cswap(a[1], a[2]); cswap(a[4], a[5]); cswap(a[7], a[8]);
+    cswap(a[0], a[1]); cswap(a[3], a[4]); cswap(a[6], a[7]);
+    if (a[0] > a[3]) a[3] = a[0];
+    if (a[3] > a[6]) a[6] = a[3];
+    cswap(a[1], a[4]);
+    if (a[4] > a[7]) a[4] = a[7];
+    if (a[1] > a[4]) a[4] = a[1];
+    if (a[5] > a[8]) a[5] = a[8];
+    if (a[2] > a[5]) a[2] = a[5];
+    cswap(a[2], a[4]);
+    if (a[4] > a[6]) a[4] = a[6];
+    if (a[2] > a[4]) a[4] = a[2];
+    return a[4];
+}
+
+// rejectBadPixels with medianDiffStats given, findstars.go:134-169.  GatherAndMedian (gather.go:26-38)
+// takes the median of the WHOLE 9-entry buffer even when fewer neighbours were in range, so entries
+// left over from the previous candidate take part at the image borders; the buffer persists here too.
+static int reject_bad_pixels(nl_star *stars, int n, const float *data, int32_t len, int32_t width, float sigma,
+                             float median_diff_stddev) {
+    const std::vector<int32_t> mask = create_mask(width, 1.5f);
+    float buffer[16] = {0};
+    const float threshold = median_diff_stddev * sigma;
+    int remaining = 0;
+    for (int i = 0; i < n; i++) {
+        const nl_star s = stars[i];
+        int num = 0;
+        for (int32_t o : mask) {
+            const int32_t io = s.index + o;
+            if (io >= 0 && io < len) buffer[num++] = data[io];
+        }
+        const float med = median9(buffer);            // the mask of radius 1.5 always has 9 entries
+        const float diff = data[s.index] - med;
+        if (diff < threshold && -diff < threshold) stars[remaining++] = s;
+    }
+    return remaining;
+}
+
+// QSortStarsDesc, star/qsort.go:25-55: unstable Hoare quicksort by mass, descending
+static void qsort_stars_desc(nl_star *a, int n) {
+    while (n > 1) {
+        const float pivot = a[(n - 1) >> 1].mass;
+        int l = -1, r = n;
+        for (;;) {
+            do l++; while (a[l].mass > pivot);
+            do r--; while (a[r].mass < pivot);
+            if (l >= r) break;
+            const nl_star t = a[l]; a[l] = a[r]; a[r] = t;
+        }
+        qsort_stars_desc(a, r + 1);     // left part recursively, right part iteratively
+        a += r + 1;
+        n -= r + 1;
+    }
+}
+
+// filterOutOverlaps, findstars.go:209-271: greedy keep in the given order; 256 px bins, each a list
+// in insertion order
+static int filter_out_overlaps(nl_star *stars, int n, int32_t width, int32_t height, int32_t radius) {
+    const int32_t bin = 256;
+    const int32_t xbins = (width + bin - 1) / bin, ybins = (height + bin - 1) / bin;
+    std::vector<std::vector<int>> bins((size_t)(xbins > 0 && ybins > 0 ? xbins * ybins : 0));
+    const int32_t r2 = radius * radius;
+    int kept = 0;
+    for (int i = 0; i < n; i++) {
+        const nl_star s = stars[i];
+        const int32_t xc = (int32_t)(s.x + 0.5f) / bin, yc = (int32_t)(s.y + 0.5f) / bin;
+        bool skip = false;
+        for (int32_t dy = -1; dy <= 1 && !skip; dy++) {
+            if (yc + dy < 0 || yc + dy >= ybins) continue;
+            for (int32_t dx = -1; dx <= 1 && !skip; dx++) {
+                if (xc + dx < 0 || xc + dx >= xbins) continue;
+                for (int j : bins[(size_t)((xc + dx) + (yc + dy) * xbins)]) {
+                    const float xd = s.x - stars[j].x, yd = s.y - stars[j].y;
+                    const int32_t sq = (int32_t)(xd * xd + yd * yd + 0.5f);
+                    if (sq <= r2) { skip = true; break; }
+                }
+            }
+        }
+        if (skip) continue;
+        stars[kept] = s;
+        // the reference indexes its bin table unguarded here (findstars.go:255) and would panic for a
+        // star whose centre left the image; such a star is kept but not binned
+        if (xc >= 0 && xc < xbins && yc >= 0 && yc < ybins) bins[(size_t)(xc + yc * xbins)].push_back(kept);
+        kept++;
+    }
+    return kept;
+}
+
+// shiftToCenterOfMass, findstars.go:274-322
+static float shift_to_center_of_mass(nl_star *stars, int n, const float *data, int32_t len, int32_t width,
+                                     float threshold, int32_t radius) {
+    float sum_of_shifts = 0.0f;
+    for (int i = 0; i < n; i++) {
+        nl_star s = stars[i];
+        float shift_sq = 3.40282346638528859811704183484516925440e+38f;
+        for (int32_t round = 0; shift_sq > 0.0001f && round < 10; round++) {
+            float xm = 0.0f, ym = 0.0f, mass = 0.0f;
+            for (int32_t y = -radius; y <= radius; y++)
+                for (int32_t x = -radius; x <= radius; x++) {
+                    const int32_t index = s.index + y * width + x;
+                    float value = 0.0f;
+                    if (index >= 0 && index < len) {
+                        value = data[index] - threshold;
+                        if (value < 0) value = 0;
+                    }
+                    xm += (float)x * value;
+                    ym += (float)y * value;
+                    mass += value;
+                }
+            const int32_t x = s.index % width, y = s.index / width;
+            if (mass == 0.0f) mass = 1e-8f;
+            const float dx = xm / mass, dy = ym / mass;
+            const float nx = (float)x + dx, ny = (float)y + dy;
+            const float pdx = nx - s.x, pdy = ny - s.y;
+            shift_sq = pdx * pdx + pdy * pdy;
+            const int32_t index = s.index + width * (int32_t)(dy + 0.5f) + (int32_t)(dx + 0.5f);
+            float value = 0.0f;
+            if (index >= 0 && index < len) value = data[index];
+            s.index = index; s.value = value; s.x = nx; s.y = ny; s.mass = mass; s.hfr = 0.0f;
+            stars[i] = s;
+        }
+        sum_of_shifts += sqrtf(shift_sq);
+    }
+    return sum_of_shifts;
+}
+
+// calcAndFilterHalfFluxRadius, findstars.go:327-396
+static int calc_and_filter_hfr(nl_star *stars, int n, const float *data, int32_t len, int32_t width, float radius,
+                               float location, float star_in_out, float *avg_hfr) {
+    int remaining = 0;
+    float avg = 0.0f;
+    for (int i = 0; i < n; i++) {
+        nl_star s = stars[i];
+        float moment = 0.0f, mass = 0.0f;
+        int32_t pixels = 0;
+        const int32_t rad = (int32_t)ceil((double)radius);
+        int32_t lim = (int32_t)ceil((double)(radius + 1e-8f) * (double)(radius + 1e-8f));
+        for (int32_t y = -rad; y <= rad; y++)
+            for (int32_t x = -rad; x <= rad; x++) {
+                const int32_t dsq = x * x + y * y;
+                if (dsq > lim) continue;
+                const float distance = (float)sqrt((double)dsq);
+                const int32_t index = s.index + y * width + x;
+                float value = 0.0f;
+                if (index >= 0 && index < len) {
+                    const float v = data[index] - location;
+                    if (v > 0) value = v;
+                }
+                moment += distance * value;
+                mass += value;
+                pixels++;
+            }
+        if (mass == 0.0f) mass = 1e-8f;
+        const float hfr = moment / mass;
+        if (hfr > radius) continue;
+        float inner_mass = 0.0f;
+        int32_t inner_pixels = 0;
+        const int32_t irad = (int32_t)ceil((double)hfr);
+        lim = (int32_t)ceil((double)(hfr * hfr));
+        for (int32_t y = -irad; y <= irad; y++)
+            for (int32_t x = -irad; x <= irad; x++) {
+                const int32_t dsq = x * x + y * y;
+                if (dsq > lim) continue;
+                const int32_t index = s.index + y * width + x;
+                float value = 0.0f;
+                if (index >= 0 && index < len) {
+                    const float v = data[index] - location;
+                    if (v > 0) value = v;
+                }
+                inner_mass += value;
+                inner_pixels++;
+            }
+        const float outer_mass = mass - inner_mass;
+        const int32_t outer_pixels = pixels - inner_pixels;
+        if (inner_mass * (float)outer_pixels <= star_in_out * outer_mass * (float)inner_pixels) continue;
+        s.hfr = hfr;
+        s.mass = mass;
+        stars[remaining++] = s;
+        avg += hfr;
+    }
+    avg /= (float)remaining;
+    *avg_hfr = avg;
+    return remaining;
+}
+
+}  // namespace nl
+
+using namespace nl;
+
+extern "C" {
+
+int nl_find_bright_dev(nl_ctx *ctx, const float *dev_data, int32_t len, int32_t width, float threshold, int32_t radius,
+                       nl_star *out, int32_t cap, int32_t *count) {
+    NL_REQUIRE(ctx && count, "NULL argument");
+    NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(out || cap == 0, "out is NULL");
+    NL_REQUIRE(dev_data || len == 0, "data is NULL");
+    CtxGuard g(ctx);
+    return find_bright_dev(ctx, dev_data, len, width, threshold, radius, out, cap, count);
+}
+
+int nl_find_bright(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float threshold, int32_t radius,
+                   nl_star *out, int32_t cap, int32_t *count) {
+    NL_REQUIRE(ctx && count, "NULL argument");
+    NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(out || cap == 0, "out is NULL");
+    NL_REQUIRE(host_data || len == 0, "data is NULL");
+    *count = 0;
+    if (len == 0) return NL_OK;
+    CtxGuard g(ctx);
+    float *dev = nullptr;
+    NL_CUDA(cudaMalloc(&dev, sizeof(float) * (size_t)len));
+    cudaError_t e = cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = e == cudaSuccess ? find_bright_dev(ctx, dev, len, width, threshold, radius, out, cap, count)
+                              : cuda_fail(e, "cudaMemcpyAsync");
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev);
+    return rc;
+}
+
+int nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float location, float scale,
+                  float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
+                  nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr) {
+    NL_REQUIRE(ctx && count && sum_of_shifts && avg_hfr, "NULL argument");
+    NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(out || cap == 0, "out is NULL");
+    // findstars.go:61: threshold = location + scale*starSig
+    const float threshold = location + scale * star_sig;
+    int32_t n = 0;
+    *count = 0; *sum_of_shifts = 0.0f; *avg_hfr = 0.0f;
+    NL_REQUIRE(host_data || len == 0, "data is NULL");
+    CtxGuard g(ctx);
+    std::vector<nl_star> stars(1);
+    if (len > 0) {
+        float *dev = nullptr;
+        NL_CUDA(cudaMalloc(&dev, sizeof(float) * (size_t)len));
+        cudaError_t e = cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
+        int rc = e == cudaSuccess ? bright_count(ctx, dev, len, width, threshold, radius, &n) : cuda_fail(e, "cudaMemcpyAsync");
+        if (rc == NL_OK) {
+            stars.resize((size_t)(n > 0 ? n : 1));
+            rc = bright_write(ctx, dev, len, width, threshold, radius, stars.data(), n);
+        }
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(dev);
+        if (rc != NL_OK) return rc;
+    }
+    int m = n;
+    if (bp_sigma > 0) m = reject_bad_pixels(stars.data(), m, host_data, len, width, bp_sigma, median_diff_stddev);
+    qsort_stars_desc(stars.data(), m);
+    m = filter_out_overlaps(stars.data(), m, width, len / width, radius);
+    *sum_of_shifts = shift_to_center_of_mass(stars.data(), m, host_data, len, width, location + scale * star_sig * 0.5f, radius);
+    qsort_stars_desc(stars.data(), m);
+    m = filter_out_overlaps(stars.data(), m, width, len / width, radius);
+    m = calc_and_filter_hfr(stars.data(), m, host_data, len, width, (float)radius, location, star_in_out, avg_hfr);
+    for (int i = 0; i < m && i < cap; i++) out[i] = stars[i];
+    *count = m;
+    return NL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// nl_synth.cu -- synthetic frame generator on the device.  Not reference
+// code: it is the workload generator of bench.py and of the full-size parity tests.  Integer
+// hashing plus dyadic fp32 only, so the CPU generator of the oracle produces identical bits.
+#include "nl_internal.h"
+
+namespace nl {
+
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU;
+    x ^= x >> 15; x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+
+__device__ __forceinline__ float synth_sample(uint32_t p, uint32_t k, uint32_t seed) {
+    const uint32_t h = lowbias32(lowbias32(p + 0x9E3779B9U * k) ^ seed);
+    float v = __fadd_rn(1024.0f, __fmul_rn((float)((int32_t)((h & 0xFFFFU) + (h >> 16)) - 65535), 1.0f / 256.0f));
+    const uint32_t h2 = lowbias32(h ^ 0xA5A5A5A5U);
+    if (h2 % 61U == 0U) v = __fadd_rn(v, 4096.0f);
+    else if (h2 % 61U == 1U) v = __fsub_rn(v, 512.0f);
+    else if (h2 % 251U == 2U) v = __int_as_float(0x7fc00000);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(float *dst, unsigned long long p0, long long count, uint32_t frame, uint32_t seed) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = synth_sample((uint32_t)(p0 + (unsigned long long)i), frame, seed);
+}
+
+}  // namespace nl
+
+using namespace nl;
+
+extern "C" int nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64_t count, uint32_t frame, uint32_t seed) {
+    NL_REQUIRE(ctx && count >= 0, "bad argument");
+    if (count == 0) return NL_OK;
+    NL_REQUIRE(dev_dst, "dst is NULL");
+    CtxGuard g(ctx);
+    long long grid = (count + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
+    synth_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_dst, p0, count, frame, seed);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}

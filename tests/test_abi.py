@@ -1,0 +1,93 @@
+"""The C-ABI library loads and exports every symbol include/nightlight_cuda.h declares; the host-only
+entry points (no device work) agree with the oracle; device entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import nightlight_b200 as nl  # noqa: E402
+from nightlight_b200 import binding  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from util import ROOT, bits_equal  # noqa: E402
+
+
+def declared_in_header():
+    text = open(os.path.join(ROOT, "include", "nightlight_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_in_header()
+    assert len(names) >= 30
+    lib = C.CDLL(nl.library_path())
+    for n in names:
+        assert hasattr(lib, n), "libnightlight_cuda.so lacks %s" % n
+    # the ctypes binding covers the header exactly
+    assert sorted(binding.DECLARED_SYMBOLS) == names
+
+
+def test_version_and_auto_mode():
+    lib = nl.load_library()
+    assert lib.nl_version() >= 100
+    # autoSelectStackingMode, stack.go:45-55
+    for n, want in ((1, 1), (5, 1), (6, 2), (14, 2), (15, 3), (24, 3), (25, 5), (1000, 5)):
+        assert lib.nl_auto_select_mode(n) == want
+
+
+def test_no_gpu_fails_loudly():
+    cnt = C.c_int(-1)
+    rc = nl.load_library().nl_device_count(C.byref(cnt))
+    if rc == 0 and cnt.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(nl.NightlightError) as e:
+        nl.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_transform_invert_matches_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        t = (rng.standard_normal(6) * np.array([1, 0.1, 50, 0.1, 1, 50])).astype(np.float32)
+        assert bits_equal(nl.transform_invert(t), O.transform_invert(t))
+    with pytest.raises(nl.NightlightError) as e:
+        nl.transform_invert([1, 2, 0, 2, 4, 0])
+    assert e.value.code == binding.NL_E_SINGULAR and "Matrix has no inverse" in str(e.value)
+
+
+def test_get_weights_matches_oracle():
+    rng = np.random.default_rng(6)
+    n = 23
+    frames = [nl.ops.Image(data=np.zeros(1, np.float32), exposure=float(rng.integers(1, 300)),
+                           noise=float(rng.random() + 0.5), hfr=float(rng.random() * 3 + 1), id=i) for i in range(n)]
+    exposure = np.array([f.exposure for f in frames], np.float32)
+    noise = np.array([f.noise for f in frames], np.float32)
+    hfr = np.array([f.hfr for f in frames], np.float32)
+    fp = C.POINTER(C.c_float)
+    for weighting in (1, 2, 3):
+        want = np.empty(n, np.float32)
+        assert O.lib().nlo_get_weights(weighting, exposure.ctypes.data_as(fp), noise.ctypes.data_as(fp),
+                                       hfr.ctypes.data_as(fp), n, want.ctypes.data_as(fp)) == 0
+        assert bits_equal(nl.get_weights(frames, weighting), want)
+    assert nl.get_weights(frames, 0) is None
+    frames[3].exposure = 0.0
+    with pytest.raises(nl.NightlightError) as e:
+        nl.get_weights(frames, 1)
+    assert "Missing exposure information" in str(e.value)
+    with pytest.raises(nl.NightlightError):
+        nl.get_weights(frames, 9)
+
+
+def test_stripe_rows_cover_image():
+    from nightlight_b200.stripes import all_stripes
+    for h in (1, 7, 8, 4096, 4097, 6000):
+        for g in (1, 2, 3, 4, 8):
+            s = all_stripes(h, g)
+            assert s[0][0] == 0 and sum(r for _, r in s) == h
+            for (a0, ar), (b0, _) in zip(s, s[1:]):
+                assert a0 + ar == b0
+            assert max(r for _, r in s) - min(r for _, r in s) <= 1

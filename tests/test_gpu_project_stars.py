@@ -1,0 +1,95 @@
+"""Parity of the resample kernel and of star detection against the oracle, through the C ABI."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import nightlight_b200 as nl  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from util import bits_equal, first_mismatch, from_hex, kats  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def star_field(w, h, nstars, seed, noise=3.0, hot=20):
+    rng = np.random.default_rng(seed)
+    img = (rng.standard_normal((h, w)) * noise + 100).astype(np.float32)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(nstars):
+        x, y = rng.uniform(0, w), rng.uniform(0, h)
+        amp, s = rng.uniform(50, 3000), rng.uniform(1.0, 3.0)
+        x0, x1, y0, y1 = int(max(0, x - 15)), int(min(w, x + 16)), int(max(0, y - 15)), int(min(h, y + 16))
+        sub = (slice(y0, y1), slice(x0, x1))
+        img[sub] += (amp * np.exp(-((xx[sub] - x) ** 2 + (yy[sub] - y) ** 2) / (2 * s * s))).astype(np.float32)
+    for _ in range(hot):                                   # single hot pixels
+        img[rng.integers(0, h), rng.integers(0, w)] += 5000
+    return img.reshape(-1)
+
+
+def test_project_kat(ctx):
+    k = kats()["project"]
+    trans = np.array([from_hex(h) for h in k["trans_hex"]], dtype=np.float32)
+    src = np.array([10 * r + c for r in range(4) for c in range(4)], dtype=np.float32)
+    out = nl.project(ctx, src, 4, 4, 4, 4, trans).reshape(4, 4)
+    want = np.array([[from_hex(h) for h in row] for row in k["rows_hex"]], dtype=np.float32)
+    assert bits_equal(out, want), first_mismatch(out, want)
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(640, 480, 640, 480), (333, 257, 400, 300), (1, 1, 5, 5), (2, 2, 3, 3), (6000, 4000, 6000, 4000)])
+def test_project_matches_oracle(ctx, sw, sh, dw, dh):
+    rng = np.random.default_rng(sw * 7 + dh)
+    src = (rng.standard_normal(sw * sh) * 100 + 1000).astype(np.float32)
+    th = np.deg2rad(rng.uniform(-3, 3))
+    for trans in ([1, 0, 0, 0, 1, 0],
+                  [np.cos(th), -np.sin(th), rng.uniform(-20, 20), np.sin(th), np.cos(th), rng.uniform(-20, 20)],
+                  [1.01, 0.02, -5.5, -0.015, 0.99, 7.25],
+                  [0.5, 0, 0.25, 0, 0.5, 0.75]):
+        trans = np.array(trans, dtype=np.float32)
+        for oob in (np.float32(np.nan), np.float32(0.0)):
+            got = nl.project(ctx, src, sw, sh, dw, dh, trans, oob)
+            want = O.project(src, sw, sh, dw, dh, trans, oob)
+            assert bits_equal(got, want), (list(trans), first_mismatch(got, want))
+
+
+def test_project_singular(ctx):
+    with pytest.raises(nl.NightlightError) as e:
+        nl.project(ctx, np.zeros(16, np.float32), 4, 4, 4, 4, [1, 2, 0, 2, 4, 0])
+    assert "Matrix has no inverse" in str(e.value)
+
+
+@pytest.mark.parametrize("w,h,radius", [(640, 480, 16), (1000, 37, 4), (257, 300, 0), (64, 3, 100), (6000, 4000, 16)])
+def test_find_bright_matches_oracle(ctx, w, h, radius):
+    img = star_field(w, h, max(5, w * h // 20000), seed=w + h)
+    for thr in (110.0, 150.0, 1e9, -1e9 if w * h < 100000 else 105.0):
+        got = nl.find_bright_pixels(ctx, img, w, thr, radius)
+        want = O.find_bright_pixels(img, w, thr, radius)
+        assert len(got) == len(want), (thr, len(got), len(want))
+        assert got.tobytes() == want.tobytes(), thr
+
+
+def test_find_bright_plateaus_and_ties(ctx):
+    """equal values keep the older candidate; a brighter one replaces it and moves the window"""
+    w, h = 300, 4
+    img = np.zeros(w * h, np.float32)
+    img[10:40] = 5.0                  # plateau
+    img[100:130] = np.arange(30)      # rising ramp: every pixel replaces the previous one
+    img[w + 50: w + 80] = np.arange(30, 0, -1)   # falling ramp
+    img[2 * w: 3 * w] = 9.0           # a whole bright row
+    for radius in (0, 1, 8, 16, 400):
+        got = nl.find_bright_pixels(ctx, img, w, 0.5, radius)
+        want = O.find_bright_pixels(img, w, 0.5, radius)
+        assert got.tobytes() == want.tobytes(), radius
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (2048, 1500)])
+def test_find_stars_matches_oracle(ctx, w, h):
+    img = star_field(w, h, w * h // 5000, seed=3 * w)
+    loc, scale = 100.0, 3.0
+    for bp_sigma, md_sd in ((0.0, 0.0), (5.0, 4.0)):
+        got = nl.find_stars(ctx, img, w, loc, scale, 15.0, bp_sigma, 1.4, 16, md_sd)
+        want = O.find_stars(img, w, loc, scale, 15.0, bp_sigma, 1.4, 16, md_sd)
+        assert len(got[0]) == len(want[0]) and len(got[0]) > 10
+        assert got[0].tobytes() == want[0].tobytes()
+        assert bits_equal([got[1], got[2]], [want[1], want[2]])

@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA stacking path, called through the C ABI, against the oracle on the
+same seeded inputs (bit-exact results, identical clip counts), the committed golden arrays, the
+reference's edge cases, and full-size (BASELINE config) runs checked on sampled tiles."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import nightlight_b200 as nl  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from util import GOLDEN, MODE_ID, bits_equal, first_mismatch, from_hex, hx, kats, mode_cases, weights_for  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_stack(ctx, frames, mode, sl=2.75, sh=2.75, w=None, ref_loc=0.0):
+    frames = np.ascontiguousarray(frames, dtype=np.float32)
+    n, p = frames.shape
+    with nl.StackJob(ctx, n, p) as job:
+        for i in range(n):
+            job.put_frame(i, frames[i])
+        return job.run(MODE_ID[mode] if isinstance(mode, str) else mode, w, sl, sh, ref_loc)
+
+
+def check_against_oracle(ctx, frames, mode, weighted, sl=2.75, sh=2.75, ref_loc=0.0, w=None):
+    if weighted and w is None:
+        w = weights_for(frames.shape[0])
+    want = O.stack(frames, mode, sl, sh, weights=w if weighted else None, ref_loc=ref_loc)
+    got = gpu_stack(ctx, frames, mode, sl, sh, w if weighted else None, ref_loc)
+    assert bits_equal(got[0], want[0]), (mode, weighted, first_mismatch(got[0], want[0]))
+    assert got[1:] == want[1:], (mode, weighted, got[1:], want[1:])
+
+
+def test_column_kats(ctx):
+    for k in kats()["columns"]:
+        col = np.array([[np.nan if v == "nan" else v for v in k["col"]]], dtype=np.float32).T
+        res, cl, ch = gpu_stack(ctx, col, k["mode"], k["sig"], k["sig"])
+        assert hx(res[0]) == k["hex"], k
+        assert [cl, ch] == k["clip"], k
+
+
+def test_golden_arrays(ctx):
+    g = np.load(os.path.join(GOLDEN, "stack_golden.npz"))
+    for n, p0, count in ((16, 0, 4096), (37, 777, 1031), (256, 4096 * 4096 - 512, 512)):
+        frames = O.synth_frames(n, p0, count)
+        w = weights_for(n)
+        for mode, weighted in mode_cases():
+            key = "n%d_p%d_c%d_%s%s" % (n, p0, count, mode, "_w" if weighted else "")
+            res, cl, ch = gpu_stack(ctx, frames, mode, w=w if weighted else None)
+            assert bits_equal(res, g[key]), (key, first_mismatch(res, g[key]))
+            assert [cl, ch] == list(g[key + "_clip"]), key
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 15, 16, 25, 64, 100, 256])
+def test_all_modes_match_oracle(ctx, n):
+    pixels = 5000 if n <= 64 else 2100           # ragged: not a multiple of 32 or of 4
+    frames = O.synth_frames(n, 31 * n, pixels)
+    for mode, weighted in mode_cases():
+        check_against_oracle(ctx, frames, mode, weighted)
+
+
+def test_config1_shape_sigma(ctx):
+    """BASELINE config 1: 16 frames of 1024x1024, sigma-clip 2.75/2.75"""
+    frames = O.synth_frames(16, 0, 1024 * 1024)
+    check_against_oracle(ctx, frames, "sigma", False)
+    check_against_oracle(ctx, frames, "auto", False)      # 16 frames -> winsorized sigma
+
+
+def test_random_data_sigmas_and_edge_pixels(ctx):
+    rng = np.random.default_rng(11)
+    for n in (6, 30, 100):
+        frames = (rng.standard_normal((n, 777)) * 50 + 1000).astype(np.float32)
+        frames[rng.random(frames.shape) < 0.02] = np.nan
+        frames[rng.random(frames.shape) < 0.03] += 2000
+        frames[:, 5] = np.nan                       # all-NaN pixel -> RefFrameLoc
+        frames[:, 6] = 7.0                          # constant pixel, sigma 0
+        frames[1:, 8] = np.nan                      # a single valid sample
+        w = rng.random(n).astype(np.float32) + np.float32(0.1)
+        for sl, sh in ((2.75, 2.75), (1.0, 3.0), (-1.0, -1.0), (0.5, 0.5)):
+            for mode, weighted in mode_cases():
+                check_against_oracle(ctx, frames, mode, weighted, sl, sh, ref_loc=0.25, w=w)
+
+
+def test_ties_and_integers(ctx):
+    rng = np.random.default_rng(12)
+    frames = rng.integers(0, 5, (64, 1000)).astype(np.float32)
+    for mode, weighted in mode_cases():
+        check_against_oracle(ctx, frames, mode, weighted)
+
+
+def test_many_frames_small_tile_path(ctx):
+    """n_frames beyond what fits 32 pixel columns per warp in shared memory (narrower tile kernels)"""
+    frames = O.synth_frames(2000, 99, 70)
+    for mode, weighted in (("sigma", False), ("median", False), ("mean", True), ("winsor", True), ("linfit", False)):
+        check_against_oracle(ctx, frames, mode, weighted)
+
+
+def test_empty_and_errors(ctx):
+    with nl.StackJob(ctx, 3, 0) as job:
+        res, cl, ch = job.run(nl.ST_SIGMA)
+        assert res.size == 0 and (cl, ch) == (0, 0)
+    frames = O.synth_frames(4, 0, 64)
+    with pytest.raises(nl.NightlightError) as e:
+        gpu_stack(ctx, frames, 7)
+    assert "invalid stacking mode" in str(e.value)
+    with pytest.raises(nl.NightlightError) as e:
+        gpu_stack(ctx, frames, -1)
+    assert "invalid stacking mode" in str(e.value)
+    with pytest.raises(nl.NightlightError) as e:
+        gpu_stack(ctx, frames, "mad", w=weights_for(4))
+    assert "MADSigma stacking with weights" in str(e.value)
+    with pytest.raises(nl.NightlightError):
+        nl.StackJob(ctx, 0, 10)
+
+
+def test_opstack_operator(ctx):
+    """OpStack.Apply semantics: auto mode, weighting from per-frame scalars, exposure sum, clip totals"""
+    n, w, h = 20, 96, 50
+    data = O.synth_frames(n, 4242, w * h)
+    frames = [nl.ops.Image(data=data[i], naxisn=(w, h), exposure=30.0 + i, noise=1.0 + 0.1 * (i % 5), hfr=2.0 + 0.05 * i, id=i)
+              for i in range(n)]
+    for weighting in (nl.W_NONE, nl.W_EXPOSURE, nl.W_INVERSE_NOISE, nl.W_INVERSE_HFR):
+        op = nl.OpStack(mode=nl.ST_AUTO, weighting=weighting, sigmaLow=2.5, sigmaHigh=3.0)
+        out = op.apply(frames, ctx)
+        wts = nl.get_weights(frames, weighting)
+        want, cl, ch = O.stack(data, "auto", 2.5, 3.0, weights=wts)
+        assert bits_equal(out.data, want), (weighting, first_mismatch(out.data, want))
+        assert (out.clip_low, out.clip_high) == (cl, ch)
+        assert out.exposure == float(np.sum([f.exposure for f in frames], dtype=np.float32))
+
+
+def test_stack_batches(ctx):
+    """stack of stacks (stackbatches.go:84-116): frame-count weighted mean of per-batch stacks"""
+    n, pixels = 30, 3000
+    data = O.synth_frames(n, 17, pixels)
+    batches = [list(range(0, 12)), list(range(12, 24)), list(range(24, 30))]
+    imgs = [[nl.ops.Image(data=data[i], naxisn=(pixels, 1), exposure=10.0) for i in b] for b in batches]
+    out = nl.OpStackBatches(perBatch=nl.OpStack(mode=nl.ST_SIGMA)).apply(imgs, ctx)
+    acc = None
+    for b in batches:
+        res, _, _ = O.stack(data[b], "sigma")
+        wgt = np.float32(len(b))
+        acc = res * wgt if acc is None else acc + res * wgt
+    want = acc * (np.float32(1.0) / np.float32(n))
+    assert bits_equal(out.data, want), first_mismatch(out.data, want)
+
+
+def test_stripes_equal_whole(ctx):
+    """row-stripe sharding: stacking each stripe separately and concatenating == stacking the image"""
+    from nightlight_b200.stripes import all_stripes
+    n, w, h = 24, 130, 37
+    data = O.synth_frames(n, 0, w * h)
+    whole = gpu_stack(ctx, data, "sigma")
+    parts, cl, ch = [], 0, 0
+    for row0, rows in all_stripes(h, 8):
+        r = gpu_stack(ctx, data[:, row0 * w:(row0 + rows) * w], "sigma")
+        parts.append(r[0]); cl += r[1]; ch += r[2]
+    assert bits_equal(np.concatenate(parts), whole[0]) and (cl, ch) == whole[1:]
+
+
+@pytest.mark.parametrize("mode,weighted,n,pixels", [
+    ("sigma", False, 256, 4096 * 4096),        # BASELINE config 2 headline: 256 x 4096^2, 16 GiB resident
+    ("winsor", True, 256, 4096 * 512),         # config 2's winsorized + weighted variant on a 512-row stripe
+    ("linfit", False, 64, 6000 * 500),
+    ("median", False, 256, 4096 * 512),
+])
+def test_full_size_sampled_tiles(ctx, mode, weighted, n, pixels):
+    """Frames generated on the device at full size; the oracle regenerates sampled tiles from the same
+    position-addressable hash and must agree bit for bit, and the clip totals must be plausible."""
+    w = weights_for(n) if weighted else None
+    with nl.StackJob(ctx, n, pixels) as job:
+        job.synth_fill(0)
+        res, cl, ch = job.run(MODE_ID[mode], w)
+    rng = np.random.default_rng(2024)
+    starts = [0, pixels - 4096] + [int(s) for s in rng.integers(0, pixels - 4096, 6)]
+    for s in starts:
+        frames = O.synth_frames(n, s, 4096)
+        want, _, _ = O.stack(frames, mode, weights=w)
+        assert bits_equal(res[s:s + 4096], want), (s, first_mismatch(res[s:s + 4096], want))
+    assert not np.isnan(res).any()
+    if mode != "median":
+        frac = (cl + ch) / (n * pixels)
+        assert 0.005 < frac < 0.5, frac
+    # size-independent property: every stacked value lies within the range of the synthetic samples
+    assert res.min() >= 1024 - 256 - 512 and res.max() <= 1024 + 256 + 4096

@@ -1,0 +1,85 @@
+"""The product's per-pixel device routines (nightlight_b200/csrc/nl_column.cuh), compiled for the CPU
+with element stride 1, against the oracle: the flattened quick-select must leave exactly the
+reference's permutation, every reducer must return the oracle's bits and clip counts."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import oracle as O  # noqa: E402
+from util import MODE_ID, bits_equal, first_mismatch, mode_cases, weights_for  # noqa: E402
+
+fp = C.POINTER(C.c_float)
+
+
+def emul_stack(L, frames, mode, sl=2.75, sh=2.75, w=None, ref_loc=0.0):
+    frames = [np.ascontiguousarray(f, dtype=np.float32) for f in frames]
+    n, p = len(frames), frames[0].size
+    ptrs = (fp * n)(*[f.ctypes.data_as(fp) for f in frames])
+    res = np.empty(p, np.float32)
+    cl, ch = C.c_longlong(), C.c_longlong()
+    wp = None
+    if w is not None:
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        wp = w.ctypes.data_as(fp)
+    rc = L.emul_stack(MODE_ID[mode], ptrs, n, p, wp, ref_loc, sl, sh, res.ctypes.data_as(fp), C.byref(cl), C.byref(ch))
+    assert rc == 0
+    return res, cl.value, ch.value
+
+
+def test_qselect_permutation(hostemul):
+    rng = np.random.default_rng(7)
+    for n in list(range(1, 70)) + [127, 128, 255, 256, 1000]:
+        for kind in range(3):
+            if kind == 0:
+                a = rng.standard_normal(n).astype(np.float32)
+            elif kind == 1:
+                a = rng.integers(0, 4, n).astype(np.float32)        # many ties
+            else:
+                a = np.sort(rng.standard_normal(n).astype(np.float32))[::-1].copy()
+            want_med, want_perm = O.qselect_median(a)
+            b = a.copy()
+            got = hostemul.emul_qselect_median(b.ctypes.data_as(fp), n)
+            assert np.float32(got) == want_med, (n, kind)
+            assert bits_equal(b, want_perm), (n, kind)
+
+
+def test_sorts(hostemul):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 17, 64, 255, 256, 1000):
+        a = rng.standard_normal(n).astype(np.float32)
+        for ins in (0, 1):
+            b = a.copy()
+            hostemul.emul_sort(b.ctypes.data_as(fp), n, ins)
+            assert np.array_equal(b, np.sort(a))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 16, 25, 64, 256])
+def test_reducers_match_oracle(hostemul, n):
+    frames = O.synth_frames(n, 1000 * n, 2048)
+    w = weights_for(n)
+    for mode, weighted in mode_cases():
+        a = O.stack(frames, mode, weights=w if weighted else None)
+        b = emul_stack(hostemul, frames, mode, w=w if weighted else None)
+        assert bits_equal(a[0], b[0]), (mode, weighted, first_mismatch(a[0], b[0]))
+        assert a[1:] == b[1:], (mode, weighted)
+
+
+def test_reducers_random_data_and_sigmas(hostemul):
+    rng = np.random.default_rng(11)
+    for n in (6, 15, 30, 100):
+        frames = (rng.standard_normal((n, 512)) * 50 + 1000).astype(np.float32)
+        frames[rng.random(frames.shape) < 0.02] = np.nan
+        frames[rng.random(frames.shape) < 0.03] += 2000
+        frames[:, 5] = np.nan                       # an all-NaN pixel
+        frames[:, 6] = 7.0                          # a constant pixel (sigma 0)
+        w = rng.random(n).astype(np.float32) + np.float32(0.1)
+        for sl, sh in ((2.75, 2.75), (1.0, 3.0), (-1.0, -1.0), (0.5, 0.5)):
+            for mode, weighted in mode_cases():
+                a = O.stack(frames, mode, sl, sh, weights=w if weighted else None, ref_loc=0.25)
+                b = emul_stack(hostemul, frames, mode, sl, sh, w if weighted else None, ref_loc=0.25)
+                assert bits_equal(a[0], b[0]), (n, sl, mode, weighted, first_mismatch(a[0], b[0]))
+                assert a[1:] == b[1:], (n, sl, mode, weighted)

@@ -1,0 +1,47 @@
+"""world_size-2 gloo test of the multi-GPU host logic: row-stripe partition, stripe all-gather with
+ragged stripes, clip-counter all-reduce.  The per-stripe stack itself is played by the oracle here
+(CPU box); on the GPU box tests/test_gpu_stack.py::test_stripes_equal_whole checks the CUDA path."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _worker(rank, world, port, width, height, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nightlight_b200.stripes import stripe_rows, allgather_image, allreduce_clip_counts
+    from oracle import oracle as O
+    row0, rows = stripe_rows(height, world, rank)
+    frames = O.synth_frames(n, row0 * width, rows * width)
+    res, cl, ch = O.stack(frames, "sigma")
+    full = allgather_image(torch.from_numpy(res), width, height)
+    tl, th = allreduce_clip_counts(cl, ch, "cpu")
+    if rank == 0:
+        q.put((full.numpy().copy(), tl, th))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_stripes_equal_whole():
+    from oracle import oracle as O
+    width, height, n, world = 37, 13, 12, 2          # ragged: 7 + 6 rows
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, width, height, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    full, tl, th = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want, cl, ch = O.stack(O.synth_frames(n, 0, width * height), "sigma")
+    assert np.array_equal(full.view(np.uint32), want.view(np.uint32))
+    assert (tl, th) == (cl, ch)
