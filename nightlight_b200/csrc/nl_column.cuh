@@ -25,6 +25,16 @@
 #define NL_HD inline
 #endif
 
+// Warp-wide "any lane" vote.  The flattened loops below keep the 32 lanes of a warp (32 different
+// pixels) in ONE loop that runs until the slowest lane is done; on the host (stride 1, one column
+// at a time) the vote is the lane's own flag.  Every routine that votes must be called by all 32
+// lanes of the warp (lanes without a pixel pass n = 0).
+#if defined(__CUDA_ARCH__)
+#define NL_ANY(x) (__any_sync(0xffffffffu, (x)))
+#else
+#define NL_ANY(x) (x)
+#endif
+
 namespace nl {
 
 NL_HD float nl_sqrtf(float x) {
@@ -74,50 +84,121 @@ NL_HD int auto_select_mode(int n_frames) {
     return ST_MEAN;
 }
 
+NL_HD int lowest_bit(unsigned x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
-// Quick-select, exact permutation of qsort.go:94-126 (Hoare partition, pivot a[(l+r)>>1]).
-// k is 1-based.  Flattened: every trip of the single loop advances the left and the right scan
-// pointer of the current partition by at most one element each, or performs one swap, or closes
-// the partition -- so 32 lanes working on 32 different columns stay converged.
-// The two scans of a Hoare round are independent (no stores happen between them), so advancing
-// them in lock step visits exactly the stop positions of the sequential code.
+// Column memory.  On the device a column lives in shared memory and is addressed by 32-bit
+// shared-window byte addresses with immediate element offsets (one LDS per access, no address
+// arithmetic); on the host (tests) it is a plain float array.  The accesses of the quick-select are
+// `volatile` asm so that loads and stores keep their program order.
 // ---------------------------------------------------------------------------------------------
 template <int S>
+struct ColMem {
+#if defined(__CUDA_ARCH__)
+    typedef unsigned pos_t;
+    static __device__ __forceinline__ pos_t at(const float *a) { return (unsigned)__cvta_generic_to_shared(a); }
+    template <int J>
+    static __device__ __forceinline__ float ld(pos_t p) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(p), "n"(J * S * 4));
+        return v;
+    }
+    static __device__ __forceinline__ void st(pos_t p, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(p), "f"(v)); }
+    static __device__ __forceinline__ pos_t add(pos_t p, int elems) { return p + (unsigned)(elems * (S * 4)); }
+    static __device__ __forceinline__ int diff(pos_t a, pos_t b) { return (int)(a - b) / (S * 4); }
+#else
+    typedef float *pos_t;
+    static pos_t at(const float *a) { return const_cast<float *>(a); }
+    template <int J>
+    static float ld(pos_t p) { return p[J * S]; }
+    static void st(pos_t p, float v) { *p = v; }
+    static pos_t add(pos_t p, int elems) { return p + elems * S; }
+    static int diff(pos_t a, pos_t b) { return (int)((a - b) / S); }
+#endif
+};
+
+// ---------------------------------------------------------------------------------------------
+// Quick-select, exact permutation of qsort.go:94-126 (Hoare partition, pivot a[(l+r)>>1]).
+// k is 1-based.
+//
+// SIMT form.  The 32 lanes of a warp run 32 different columns, so the nested data-dependent loops
+// of the reference are flattened into ONE loop of branch-free steps that all lanes execute until
+// the slowest is done.  The two scans of a Hoare round are independent (nothing is stored between
+// them), so they advance in lock step.  Every step looks at a window of QW samples under each
+// scan pointer: a pointer that is not at a stop jumps to the first stop inside its window (or
+// over the whole window); when both pointers are at their stops and have not crossed, the step
+// swaps the two samples and keeps scanning the rest of the two windows.  The windows were loaded
+// before the swap was stored, which is only a problem when the pointers are closer than a window
+// (`near`): then the step advances by the one slot the swap itself consumes and the next step
+// re-reads memory.  Window slots beyond a scan's guaranteed stop (the pivot slot, or a slot
+// swapped earlier) may lie outside the partition or even the column (callers pad QW-1 slots on
+// both sides of the buffers); their flags are never used.  A lane whose scans have crossed idles
+// until the next check for finished partitions; a lane whose selection is finished, or that has
+// no samples, is parked on slot 0 (l == r, pivot = a[0], which must not be a NaN: callers store a
+// 0 there for an empty column).  GATE adds an explicit `active` term for lanes that alias another
+// lane's column (narrow tiles).
+// ---------------------------------------------------------------------------------------------
+constexpr int QW = 4;
+
+template <int S, bool GATE = false>
 NL_HD float qselect(float *a, int n, int k) {
-    int left = 0, right = n - 1;
-    if (left >= right) return a[left * S];
-    float pivot = a[((left + right) >> 1) * S];
-    int l = left, r = right;
-    for (;;) {
-        float al = a[l * S], ar = a[r * S];
-        bool sl = al >= pivot;   // left scan stops here
-        bool sr = ar <= pivot;   // right scan stops here
-        if (sl && sr) {
-            if (l < r) {          // swap, both scans move on
-                a[l * S] = ar;
-                a[r * S] = al;
-                l++; r--;
-            } else {              // scans crossed: partition index is r
-                int offset = r - left + 1;
+    typedef ColMem<S> M;
+    typedef typename M::pos_t P;
+    P left = M::at(a), right = M::add(left, n > 0 ? n - 1 : 0);
+    bool active = n > 1;
+    P l = left, r = right;
+    float pivot = M::template ld<0>(M::add(left, (n > 0 ? n - 1 : 0) >> 1));
+    while (NL_ANY(active)) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const float l0 = M::template ld<0>(l), l1 = M::template ld<1>(l), l2 = M::template ld<2>(l), l3 = M::template ld<3>(l);
+            const float r0 = M::template ld<0>(r), r1 = M::template ld<-1>(r), r2 = M::template ld<-2>(r), r3 = M::template ld<-3>(r);
+            const bool sl = l0 >= pivot;                     // left scan stops here  (qsort.go:104-108)
+            const bool sr = r0 <= pivot;                     // right scan stops here (qsort.go:109-113)
+            int tl = (l3 >= pivot) ? 3 : 4;                  // first stop among the window slots 1..3
+            tl = (l2 >= pivot) ? 2 : tl;
+            tl = (l1 >= pivot) ? 1 : tl;
+            int tr = (r3 <= pivot) ? 3 : 4;
+            tr = (r2 <= pivot) ? 2 : tr;
+            tr = (r1 <= pivot) ? 1 : tr;
+            const int d = M::diff(r, l);
+            const bool sw = sl & sr & (d > 0);               // both stopped, not crossed: swap (qsort.go:114-115)
+            if (sw) { M::st(l, r0); M::st(r, l0); }
+            const bool near = d < QW;                        // the windows saw slots the swap has just changed
+            const int step = (sw & near) ? 1 : 0;
+            int dl = (!sl | sw) ? (step ? 1 : tl) : 0;
+            int dr = (!sr | sw) ? (step ? 1 : tr) : 0;
+            if (GATE) { dl = active ? dl : 0; dr = active ? dr : 0; }
+            l = M::add(l, dl);
+            r = M::add(r, -dr);
+        }
+        const bool cross = active & (M::template ld<0>(l) >= pivot) & (M::template ld<0>(r) <= pivot) & !(l < r);
+        if (NL_ANY(cross)) {                                 // qsort.go:114: partition index = r
+            if (cross) {
+                const int offset = M::diff(r, left) + 1;
                 if (k <= offset) right = r;
-                else { left = r + 1; k -= offset; }
-                if (left >= right) break;
-                pivot = a[((left + right) >> 1) * S];
-                l = left; r = right;
+                else { left = M::add(r, 1); k -= offset; }
+                active = left < right;
+                pivot = M::template ld<0>(M::add(left, M::diff(right, left) >> 1));
+                l = left;
+                r = active ? right : left;
             }
-        } else {
-            l += sl ? 0 : 1;
-            r -= sr ? 0 : 1;
         }
     }
-    return a[left * S];
+    return M::template ld<0>(left);
 }
 
 // qsort.go:68-82 QSelectMedianFloat32
-template <int S>
+template <int S, bool GATE = false>
 NL_HD float qselect_median(float *a, int n) {
     int k = (n >> 1) + 1;
-    float upper = qselect<S>(a, n, k);
+    float upper = qselect<S, GATE>(a, n, k);
     if (n & 1) return upper;
     float lower = a[0];
     for (int i = 1; i < k - 1; i++) lower = fmaxf(lower, a[i * S]);   // no NaNs in a column
@@ -146,19 +227,36 @@ NL_HD void mean_stddev(const float *a, int n, float &mean, float &sd) {
 // The clip loop shared by the sigma and winsor variants (stack.go:411-424, 495-514, 674-689,
 // 779-798): an out-of-bounds sample is overwritten by the last one, the slice shrinks and slot j
 // is tested again.  W: weights travel with the values.
+// SIMT form: samples that are in bounds are only ever stepped over by the reference loop, so the
+// buffer is scanned 32 slots at a time into a bit mask of out-of-bounds slots (regular, branch
+// free), and only the set bits are then resolved one by one in ascending order exactly like the
+// reference does (replace by the last sample, re-test the slot, stop at the shrinking end).
+// Reads up to 31 slots past `cur`: buffers are padded to a multiple of 32 slots.
 template <int S, bool W>
 NL_HD int clip_pass(float *g, float *gw, int cur, float lo, float hi, int &ncl, int &nch) {
-    int j = 0;
-    while (j < cur) {
-        float v = g[j * S];
-        bool low = v < lo, high = v > hi;
-        if (low || high) {
-            cur--;
-            g[j * S] = g[cur * S];
-            if (W) gw[j * S] = gw[cur * S];
-            if (low) ncl++; else nch++;
-        } else {
-            j++;
+    for (int b = 0; NL_ANY(b < cur); b += 32) {
+        unsigned bad = 0;
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            const float v = g[(b + u) * S];
+            bad |= ((v < lo) | (v > hi)) ? (1u << u) : 0u;
+        }
+        const int rem = cur - b;
+        bad &= rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+        while (NL_ANY(bad != 0)) {
+            if (bad != 0) {
+                const int j = b + lowest_bit(bad);
+                if (j >= cur) {
+                    bad = 0;                            // the slice has shrunk below the remaining slots
+                } else {
+                    if (g[j * S] < lo) ncl++; else nch++;   // a set bit means slot j is out of bounds
+                    cur--;
+                    const float t = g[cur * S];         // g[j] = g[last]; shrink; test slot j again
+                    g[j * S] = t;
+                    if (W) gw[j * S] = gw[cur * S];
+                    if (!((t < lo) | (t > hi)) | (j >= cur)) bad &= bad - 1;
+                }
+            }
         }
     }
     return cur;
@@ -283,42 +381,63 @@ NL_HD void ramp_mean_stddev(int n, float &mean, float &sd) {
 // stack.go:372-436 StackSigma / stack.go:442-531 StackSigmaWeighted.  In the weighted variant the
 // quick-select permutes the values but not the weights (stack.go:487 hands it gatheredCur only);
 // the weights move in the clip loop alone.  Reproduced as is.
+// All 32 lanes of a warp call these together (the quick-select and the clip pass vote); `cur` may
+// be 0 for a lane without samples, whose result is then meaningless.  A lane that has finished
+// keeps walking through the remaining passes of its neighbours with an empty column.
 template <int S, bool W>
 NL_HD float reduce_sigma(float *g, float *gw, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
-    for (;;) {
-        float median = qselect_median<S>(g, cur);
+    bool done = cur == 0;
+    float result = 0.0f;
+    while (NL_ANY(!done)) {
+        const int m = done ? 0 : cur;
+        const float median = qselect_median<S, (S < 32)>(g, m);
         float mean, sd;
-        mean_stddev<S>(g, cur, mean, sd);
-        float lo = nl_subf(median, nl_mulf(sig_lo, sd));
-        float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-        int before = cur;
-        cur = clip_pass<S, W>(g, gw, cur, lo, hi, ncl, nch);
-        if (cur == before || cur <= 1) return W ? weighted_mean<S>(g, gw, cur) : mean;
+        mean_stddev<S>(g, m, mean, sd);
+        const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
+        const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
+        const int left = clip_pass<S, W>(g, gw, m, lo, hi, ncl, nch);
+        if (!done) {
+            if (left == cur || left <= 1) {
+                result = W ? weighted_mean<S>(g, gw, left) : mean;
+                done = true;
+            }
+            cur = left;
+        }
     }
+    return result;
 }
 
 // stack.go:611-705 StackWinsorSigma / stack.go:710-829 StackWinsorSigmaWeighted
 template <int S, bool W>
 NL_HD float reduce_winsor(float *g, float *gw, float *wz, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
-    for (;;) {
-        float median = qselect_median<S>(g, cur);
+    bool done = cur == 0;
+    float result = 0.0f;
+    while (NL_ANY(!done)) {
+        const int m = done ? 0 : cur;
+        const float median = qselect_median<S, (S < 32)>(g, m);
         float mean, sd;
-        mean_stddev<S>(g, cur, mean, sd);
-        sd = winsor_sigma<S>(g, wz, cur, median, sd);
-        float lo = nl_subf(median, nl_mulf(sig_lo, sd));
-        float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-        int before = cur;
-        cur = clip_pass<S, W>(g, gw, cur, lo, hi, ncl, nch);
-        if (cur == before || cur <= 1) return W ? weighted_mean<S>(g, gw, cur) : mean;
+        mean_stddev<S>(g, m, mean, sd);
+        if (m > 0) sd = winsor_sigma<S>(g, wz, m, median, sd);
+        const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
+        const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
+        const int left = clip_pass<S, W>(g, gw, m, lo, hi, ncl, nch);
+        if (!done) {
+            if (left == cur || left <= 1) {
+                result = W ? weighted_mean<S>(g, gw, left) : mean;
+                done = true;
+            }
+            cur = left;
+        }
     }
+    return result;
 }
 
 // stack.go:536-605 StackMADSigma (single pass; 0/0 -> NaN when everything is clipped, as in Go)
 template <int S>
 NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
-    float median = qselect_median<S>(g, cur);
+    float median = qselect_median<S, (S < 32)>(g, cur);
     for (int i = 0; i < cur; i++) ad[i * S] = fabsf(nl_subf(g[i * S], median));
-    float mad = qselect_median<S>(ad, cur);
+    float mad = qselect_median<S, (S < 32)>(ad, cur);
     float sd = nl_mulf(mad, 1.4826f);
     float lo = nl_subf(median, nl_mulf(sig_lo, sd));
     float hi = nl_addf(median, nl_mulf(sig_hi, sd));

@@ -32,6 +32,7 @@ struct StackArgs {
     float ref_loc, sig_lo, sig_hi;
     float *out;              // [pixels]
     unsigned long long *clip;   // [2] low, high
+    unsigned long long *tile_counter;   // next tile of the dynamic scheduler (zeroed per launch)
 };
 
 __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
@@ -86,33 +87,41 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
     const int n = a.n;
+    const int npad = (n + 31) & ~31;                              // clip_pass scans whole 32-slot blocks
     constexpr int NB = ColumnBufs<MODE, W>::value;
-    float *g = smem + (size_t)warp * NB * S * n + lane;          // column element i at g[i*S]
-    float *gw = W ? g + (size_t)S * n : nullptr;
-    float *sc = g + (size_t)(W ? 2 : 1) * S * n;                  // winsor / MAD scratch
+    // column element i of this lane's pixel at g[i*S]; lanes beyond a narrow tile alias a valid
+    // column but never get samples (cur = 0) and never store
+    // (QW-1 rows of padding in front of the first and behind the last column buffer: the quick-select
+    // windows may read, never use, up to QW-1 slots outside a column)
+    float *g = smem + (size_t)(QW - 1) * S + (size_t)warp * NB * S * npad + (lane % S);
+    float *gw = W ? g + (size_t)S * npad : nullptr;
+    float *sc = g + (size_t)(W ? 2 : 1) * S * npad;              // winsor / MAD scratch
     (void)sc;
 
     const long long tiles = (a.pixels + S - 1) / S;
-    const long long warp_gid = (long long)blockIdx.x * warps_per_cta + warp;
-    const long long warp_cnt = (long long)gridDim.x * warps_per_cta;
     int ncl = 0, nch = 0;
 
-    for (long long t = warp_gid; t < tiles; t += warp_cnt) {
-        const long long p = t * S + lane;
-        const bool active = lane < S && p < a.pixels;
-        if (active) {
-            // gather the non-NaN samples of pixel p in frame order (stack.go:380-387)
+    for (;;) {
+        // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long long)t >= tiles) break;
+        const long long p = (long long)t * S + lane;
+        const bool valid = lane < S && p < a.pixels;
+        int cur = 0;
+        if (valid) {
+            // gather the non-NaN samples of pixel p in frame order (stack.go:380-387): 16 loads
+            // in flight per lane, each a 128-byte row segment per warp
             const float *src = a.frames + p;
-            int cur = 0;
             int k = 0;
-            for (; k + 8 <= n; k += 8) {
-                float v[8];
+            for (; k + 16 <= n; k += 16) {
+                float v[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = ld_stream(src + (long long)(k + u) * a.stride);
+                for (int u = 0; u < 16; u++) v[u] = ld_stream(src + (long long)(k + u) * a.stride);
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < 16; u++) {
                     g[cur * S] = v[u];
                     if (W) gw[cur * S] = __ldg(a.weights + k + u);
                     cur += (v[u] == v[u]) ? 1 : 0;
@@ -126,22 +135,22 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
                     cur++;
                 }
             }
-            float res;
-            if (cur == 0) {
-                res = a.ref_loc;                                   // stack.go:388-397
-            } else if (MODE == ST_MEDIAN) {
-                res = qselect_median<S>(g, cur);                   // stack.go:274-303
-            } else if (MODE == ST_SIGMA) {
-                res = reduce_sigma<S, W>(g, gw, cur, a.sig_lo, a.sig_hi, ncl, nch);
-            } else if (MODE == ST_WINSOR) {
-                res = reduce_winsor<S, W>(g, gw, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
-            } else if (MODE == ST_MAD) {
-                res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
-            } else {
-                res = reduce_linfit<S>(g, cur, a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
-            }
-            a.out[p] = res;
         }
+        if (cur == 0 && lane < S) g[0] = 0.0f;                    // parked lanes compare slot 0 with itself
+        __syncwarp();
+        float res;
+        if (MODE == ST_MEDIAN) {
+            res = qselect_median<S, (S < 32)>(g, cur);                       // stack.go:274-303
+        } else if (MODE == ST_SIGMA) {
+            res = reduce_sigma<S, W>(g, gw, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else if (MODE == ST_WINSOR) {
+            res = reduce_winsor<S, W>(g, gw, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else if (MODE == ST_MAD) {
+            res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else {
+            res = cur > 0 ? reduce_linfit<S>(g, cur, a.ramp, a.sig_lo, a.sig_hi, ncl, nch) : 0.0f;
+        }
+        if (valid) a.out[p] = cur == 0 ? a.ref_loc : res;         // stack.go:388-397
         __syncwarp();
     }
     if (MODE >= ST_SIGMA) {
@@ -181,7 +190,7 @@ struct nl_stack_job {
     float *weights = nullptr;         // [n]
     float *ramp = nullptr;            // [2*(n+1)]
     bool ramp_ready = false;
-    unsigned long long *clip = nullptr;   // [2] device
+    unsigned long long *clip = nullptr;   // [3] device: clip low, clip high, tile counter
     unsigned long long *clip_host = nullptr;   // [2] pinned
 };
 
@@ -191,12 +200,14 @@ template <int MODE, bool W, int S>
 static int launch_column(nl_stack_job *job, const StackArgs &args) {
     nl_ctx *ctx = job->ctx;
     constexpr int NB = ColumnBufs<MODE, W>::value;
-    const size_t per_warp = (size_t)NB * S * job->n * sizeof(float);
+    const size_t per_warp = (size_t)NB * S * ((job->n + 31) & ~31) * sizeof(float);
     const size_t cap = (size_t)ctx->max_smem_optin;
-    if (per_warp > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
+    if (per_warp + (size_t)2 * (QW - 1) * S * sizeof(float) > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
     int warps = (int)(cap / per_warp);
     if (warps > 8) warps = 8;
-    const size_t smem = per_warp * warps;
+    const size_t pad = (size_t)2 * (QW - 1) * S * sizeof(float);
+    if (warps > 1 && per_warp * warps + pad > cap) warps--;
+    const size_t smem = per_warp * warps + pad;
     auto kern = stack_column_kernel<MODE, W, S>;
     NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
@@ -216,10 +227,11 @@ static int launch_column(nl_stack_job *job, const StackArgs &args) {
 template <int MODE, bool W>
 static int launch_column_s(nl_stack_job *job, const StackArgs &args) {
     constexpr int NB = ColumnBufs<MODE, W>::value;
-    const size_t per_pixel = (size_t)NB * job->n * sizeof(float);
+    const size_t per_pixel = (size_t)NB * ((job->n + 31) & ~31) * sizeof(float);
     const size_t cap = (size_t)job->ctx->max_smem_optin;
-    if (per_pixel * 32 <= cap) return launch_column<MODE, W, 32>(job, args);
-    if (per_pixel * 8 <= cap) return launch_column<MODE, W, 8>(job, args);
+    const size_t pad = (size_t)2 * (QW - 1) * sizeof(float);
+    if ((per_pixel + pad) * 32 <= cap) return launch_column<MODE, W, 32>(job, args);
+    if ((per_pixel + pad) * 8 <= cap) return launch_column<MODE, W, 8>(job, args);
     return launch_column<MODE, W, 1>(job, args);
 }
 
@@ -247,7 +259,7 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     const bool weighted = host_weights != nullptr;
     if (mode == NL_ST_MAD_SIGMA && weighted)
         return set_error(NL_E_UNSUPPORTED, "MADSigma stacking with weights is still unimplemented");         // stack.go:185
-    NL_CUDA(cudaMemsetAsync(job->clip, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    NL_CUDA(cudaMemsetAsync(job->clip, 0, 3 * sizeof(unsigned long long), ctx->stream));
     if (job->pixels == 0) return NL_OK;
     if (weighted)
         NL_CUDA(cudaMemcpyAsync(job->weights, host_weights, sizeof(float) * job->n, cudaMemcpyHostToDevice, ctx->stream));
@@ -260,7 +272,7 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     StackArgs a;
     a.frames = job->frames; a.stride = job->pixels; a.pixels = job->pixels; a.n = job->n;
     a.weights = weighted ? job->weights : nullptr; a.ramp = job->ramp;
-    a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip;
+    a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip; a.tile_counter = job->clip + 2;
     switch (mode) {
     case NL_ST_MEDIAN: return launch_column_s<ST_MEDIAN, false>(job, a);     // weights ignored, stack.go:160-161
     case NL_ST_MEAN: return weighted ? launch_mean<true>(job, a) : launch_mean<false>(job, a);
@@ -319,7 +331,7 @@ int nl_stack_begin(nl_ctx *ctx, int32_t n_frames, int64_t pixels, nl_stack_job *
     if (e == cudaSuccess) e = cudaMalloc(&j->out, sizeof(float) * (size_t)(pixels > 0 ? pixels : 1));
     if (e == cudaSuccess) e = cudaMalloc(&j->weights, sizeof(float) * (size_t)n_frames);
     if (e == cudaSuccess) e = cudaMalloc(&j->ramp, sizeof(float) * 2 * ((size_t)n_frames + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&j->clip, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&j->clip, 3 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&j->clip_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         nl_stack_end(j);

@@ -10,7 +10,9 @@ using namespace nl;
 extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t len, const float *weights,
                           float ref_loc, float sig_lo, float sig_hi, float *res, long long *clip_lo, long long *clip_hi) {
     if (mode == ST_AUTO) mode = auto_select_mode(n);
-    std::vector<float> g(n + 1), gw(n + 1), wz(n + 1), ramp(2 * (n + 2));
+    // clip_pass reads whole 32-slot blocks; the quick-select windows read QW-1 slots outside a column
+    std::vector<float> g_(n + 40), gw_(n + 40), wz_(n + 40), ramp(2 * (n + 2));
+    float *g = g_.data() + 4, *gw = gw_.data() + 4, *wz = wz_.data() + 4;
     for (int c = 1; c <= n; c++) ramp_mean_stddev(c, ramp[2 * c], ramp[2 * c + 1]);
     long long tl = 0, th = 0;
     bool W = weights != nullptr;
@@ -38,17 +40,17 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
         }
         if (cur == 0) { res[p] = ref_loc; continue; }
         switch (mode) {
-        case ST_MEDIAN: out = qselect_median<1>(g.data(), cur); break;
+        case ST_MEDIAN: out = qselect_median<1, true>(g, cur); break;
         case ST_SIGMA:
-            out = W ? reduce_sigma<1, true>(g.data(), gw.data(), cur, sig_lo, sig_hi, ncl, nch)
-                    : reduce_sigma<1, false>(g.data(), nullptr, cur, sig_lo, sig_hi, ncl, nch);
+            out = W ? reduce_sigma<1, true>(g, gw, cur, sig_lo, sig_hi, ncl, nch)
+                    : reduce_sigma<1, false>(g, nullptr, cur, sig_lo, sig_hi, ncl, nch);
             break;
         case ST_WINSOR:
-            out = W ? reduce_winsor<1, true>(g.data(), gw.data(), wz.data(), cur, sig_lo, sig_hi, ncl, nch)
-                    : reduce_winsor<1, false>(g.data(), nullptr, wz.data(), cur, sig_lo, sig_hi, ncl, nch);
+            out = W ? reduce_winsor<1, true>(g, gw, wz, cur, sig_lo, sig_hi, ncl, nch)
+                    : reduce_winsor<1, false>(g, nullptr, wz, cur, sig_lo, sig_hi, ncl, nch);
             break;
-        case ST_MAD: out = reduce_mad<1>(g.data(), wz.data(), cur, sig_lo, sig_hi, ncl, nch); break;
-        case ST_LINFIT: out = reduce_linfit<1>(g.data(), cur, ramp.data(), sig_lo, sig_hi, ncl, nch); break;
+        case ST_MAD: out = reduce_mad<1>(g, wz, cur, sig_lo, sig_hi, ncl, nch); break;
+        case ST_LINFIT: out = reduce_linfit<1>(g, cur, ramp.data(), sig_lo, sig_hi, ncl, nch); break;
         default: return -1;
         }
         res[p] = out;
@@ -59,5 +61,11 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
 }
 
 // permutation check: run the flattened quick-select and hand back the permuted buffer
-extern "C" float emul_qselect_median(float *a, int n) { return qselect_median<1>(a, n); }
+extern "C" float emul_qselect_median(float *a, int n) {
+    std::vector<float> b(n + 8, 0.0f);
+    for (int i = 0; i < n; i++) b[4 + i] = a[i];
+    float m = qselect_median<1, true>(b.data() + 4, n);
+    for (int i = 0; i < n; i++) a[i] = b[4 + i];
+    return m;
+}
 extern "C" void emul_sort(float *a, int n, int insertion) { if (insertion) insertion_sort_column<1>(a, n); else sort_column<1>(a, n); }
