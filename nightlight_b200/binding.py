@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libnightlight_cuda.so")
+# NL_CUDA_LIB: development override to A/B-test another build of the same library
+_SO = os.environ.get("NL_CUDA_LIB") or os.path.join(_HERE, "libnightlight_cuda.so")
 
 ST_MEDIAN, ST_MEAN, ST_SIGMA, ST_WINSOR_SIGMA, ST_MAD_SIGMA, ST_LINEAR_FIT, ST_AUTO = range(7)
 W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR = range(4)

@@ -145,6 +145,10 @@ struct ColMem {
 // lane's column (narrow tiles).
 // ---------------------------------------------------------------------------------------------
 constexpr int QW = 4;
+#ifndef NL_QSTEPS
+#define NL_QSTEPS 4
+#endif
+constexpr int QSTEPS = NL_QSTEPS;   // steps between two checks for crossed scans
 
 template <int S, bool GATE = false>
 NL_HD float qselect(float *a, int n, int k) {
@@ -154,9 +158,10 @@ NL_HD float qselect(float *a, int n, int k) {
     bool active = n > 1;
     P l = left, r = right;
     float pivot = M::template ld<0>(M::add(left, (n > 0 ? n - 1 : 0) >> 1));
-    while (NL_ANY(active)) {
+    bool any_active = NL_ANY(active);
+    while (any_active) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < QSTEPS; u++) {
             const float l0 = M::template ld<0>(l), l1 = M::template ld<1>(l), l2 = M::template ld<2>(l), l3 = M::template ld<3>(l);
             const float r0 = M::template ld<0>(r), r1 = M::template ld<-1>(r), r2 = M::template ld<-2>(r), r3 = M::template ld<-3>(r);
             const bool sl = l0 >= pivot;                     // left scan stops here  (qsort.go:104-108)
@@ -189,6 +194,7 @@ NL_HD float qselect(float *a, int n, int k) {
                 l = left;
                 r = active ? right : left;
             }
+            any_active = NL_ANY(active);                     // lanes only ever finish in here
         }
     }
     return M::template ld<0>(left);
