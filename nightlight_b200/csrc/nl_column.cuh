@@ -232,14 +232,16 @@ NL_HD void mean_stddev(const float *a, int n, float &mean, float &sd) {
 
 // The clip loop shared by the sigma and winsor variants (stack.go:411-424, 495-514, 674-689,
 // 779-798): an out-of-bounds sample is overwritten by the last one, the slice shrinks and slot j
-// is tested again.  W: weights travel with the values.
+// is tested again.  W: weights travel with the values -- as the FRAME INDEX of every sample (IDX =
+// uint8_t up to 256 frames, else uint16_t), a quarter / half of the shared memory an fp32 copy of
+// the weights would take; the weight itself is looked up when the weighted mean is formed.
 // SIMT form: samples that are in bounds are only ever stepped over by the reference loop, so the
 // buffer is scanned 32 slots at a time into a bit mask of out-of-bounds slots (regular, branch
 // free), and only the set bits are then resolved one by one in ascending order exactly like the
 // reference does (replace by the last sample, re-test the slot, stop at the shrinking end).
 // Reads up to 31 slots past `cur`: buffers are padded to a multiple of 32 slots.
-template <int S, bool W>
-NL_HD int clip_pass(float *g, float *gw, int cur, float lo, float hi, int &ncl, int &nch) {
+template <int S, bool W, typename IDX>
+NL_HD int clip_pass(float *g, IDX *gw, int cur, float lo, float hi, int &ncl, int &nch) {
     for (int b = 0; NL_ANY(b < cur); b += 32) {
         unsigned bad = 0;
 #pragma unroll
@@ -268,46 +270,61 @@ NL_HD int clip_pass(float *g, float *gw, int cur, float lo, float hi, int &ncl, 
     return cur;
 }
 
-// weighted mean of the survivors in buffer order (stack.go:518-524, 802-808)
-template <int S>
-NL_HD float weighted_mean(const float *g, const float *gw, int cur) {
+// weighted mean of the survivors in buffer order (stack.go:518-524, 802-808); gw = frame index of
+// every surviving sample, wtab = the per-frame weights
+template <int S, typename IDX>
+NL_HD float weighted_mean(const float *g, const IDX *gw, const float *wtab, int cur) {
     float ws = 0.0f, wsum = 0.0f;
     for (int i = 0; i < cur; i++) {
-        float w = gw[i * S];
+#if defined(__CUDA_ARCH__)
+        float w = __ldg(wtab + gw[i * S]);
+#else
+        float w = wtab[gw[i * S]];
+#endif
         ws = nl_addf(ws, nl_mulf(g[i * S], w));
         wsum = nl_addf(wsum, w);
     }
     return nl_divf(ws, wsum);
 }
 
-// inner winsorisation loop (stack.go:649-672, 754-777); wz is scratch of the same shape as g
+// inner winsorisation loop (stack.go:649-672, 754-777).  The reference clamps a COPY of the column
+// again and again; a composition of clamps onto intervals is itself a clamp, onto
+// [clamp(L,lo,hi), clamp(H,lo,hi)], and clamping never rounds, so the copy after any number of rounds
+// is clamp(g[i], L, H) with the cumulative bounds (L, H) -- recomputed on the fly here, which saves
+// the second shared-memory buffer (and its traffic) the copy would need.  `changed` counts, like the
+// reference, the samples the CURRENT round moved.
+NL_HD float clampcmp(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 template <int S>
-NL_HD float winsor_sigma(const float *g, float *wz, int cur, float median, float sd) {
-    for (int i = 0; i < cur; i++) wz[i * S] = g[i * S];
+NL_HD float winsor_sigma(const float *g, int cur, float median, float sd) {
+    float L = -INFINITY, H = INFINITY;
     for (;;) {
-        float lo = nl_subf(median, nl_mulf(1.5f, sd));
-        float hi = nl_addf(median, nl_mulf(1.5f, sd));
+        const float lo = nl_subf(median, nl_mulf(1.5f, sd));
+        const float hi = nl_addf(median, nl_mulf(1.5f, sd));
         int changed = 0;
         // clamp and first sum of MeanStdDev fused: the sum runs over the clamped values in order
         float s = 0.0f;
+#pragma unroll 4
         for (int i = 0; i < cur; i++) {
-            float v = wz[i * S];
-            if (v < lo) { v = lo; changed++; wz[i * S] = v; }
-            else if (v > hi) { v = hi; changed++; wz[i * S] = v; }
+            float v = clampcmp(g[i * S], L, H);          // the copy as the previous rounds left it
+            if (v < lo) { v = lo; changed++; }
+            else if (v > hi) { v = hi; changed++; }
             s = nl_addf(s, v);
         }
-        float fn = (float)cur;
-        float m = nl_divf(s, fn);
+        L = clampcmp(L, lo, hi);
+        H = clampcmp(H, lo, hi);
+        const float fn = (float)cur;
+        const float m = nl_divf(s, fn);
         float var = 0.0f;
 #pragma unroll 8
         for (int i = 0; i < cur; i++) {
-            float d = nl_subf(wz[i * S], m);
+            const float d = nl_subf(clampcmp(g[i * S], L, H), m);
             var = nl_addf(var, nl_mulf(d, d));
         }
         var = nl_divf(var, fn);
-        float old = sd;
+        const float old = sd;
         sd = nl_mulf(1.134f, nl_sqrtf(var));
-        float factor = nl_divf(fabsf(nl_subf(sd, old)), old);
+        const float factor = nl_divf(fabsf(nl_subf(sd, old)), old);
         if (changed == 0 || factor <= 0.0005f) break;
     }
     return sd;
@@ -390,8 +407,8 @@ NL_HD void ramp_mean_stddev(int n, float &mean, float &sd) {
 // All 32 lanes of a warp call these together (the quick-select and the clip pass vote); `cur` may
 // be 0 for a lane without samples, whose result is then meaningless.  A lane that has finished
 // keeps walking through the remaining passes of its neighbours with an empty column.
-template <int S, bool W>
-NL_HD float reduce_sigma(float *g, float *gw, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
+template <int S, bool W, typename IDX>
+NL_HD float reduce_sigma(float *g, IDX *gw, const float *wtab, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
     bool done = cur == 0;
     float result = 0.0f;
     while (NL_ANY(!done)) {
@@ -401,10 +418,10 @@ NL_HD float reduce_sigma(float *g, float *gw, int cur, float sig_lo, float sig_h
         mean_stddev<S>(g, m, mean, sd);
         const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
         const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-        const int left = clip_pass<S, W>(g, gw, m, lo, hi, ncl, nch);
+        const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch);
         if (!done) {
             if (left == cur || left <= 1) {
-                result = W ? weighted_mean<S>(g, gw, left) : mean;
+                result = W ? weighted_mean<S, IDX>(g, gw, wtab, left) : mean;
                 done = true;
             }
             cur = left;
@@ -414,8 +431,8 @@ NL_HD float reduce_sigma(float *g, float *gw, int cur, float sig_lo, float sig_h
 }
 
 // stack.go:611-705 StackWinsorSigma / stack.go:710-829 StackWinsorSigmaWeighted
-template <int S, bool W>
-NL_HD float reduce_winsor(float *g, float *gw, float *wz, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
+template <int S, bool W, typename IDX>
+NL_HD float reduce_winsor(float *g, IDX *gw, const float *wtab, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
     bool done = cur == 0;
     float result = 0.0f;
     while (NL_ANY(!done)) {
@@ -423,13 +440,13 @@ NL_HD float reduce_winsor(float *g, float *gw, float *wz, int cur, float sig_lo,
         const float median = qselect_median<S, (S < 32)>(g, m);
         float mean, sd;
         mean_stddev<S>(g, m, mean, sd);
-        if (m > 0) sd = winsor_sigma<S>(g, wz, m, median, sd);
+        if (m > 0) sd = winsor_sigma<S>(g, m, median, sd);
         const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
         const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-        const int left = clip_pass<S, W>(g, gw, m, lo, hi, ncl, nch);
+        const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch);
         if (!done) {
             if (left == cur || left <= 1) {
-                result = W ? weighted_mean<S>(g, gw, left) : mean;
+                result = W ? weighted_mean<S, IDX>(g, gw, wtab, left) : mean;
                 done = true;
             }
             cur = left;
@@ -447,7 +464,7 @@ NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi,
     float sd = nl_mulf(mad, 1.4826f);
     float lo = nl_subf(median, nl_mulf(sig_lo, sd));
     float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-    cur = clip_pass<S, false>(g, nullptr, cur, lo, hi, ncl, nch);
+    cur = clip_pass<S, false, unsigned char>(g, nullptr, cur, lo, hi, ncl, nch);
     float s = 0.0f;
     for (int i = 0; i < cur; i++) s = nl_addf(s, g[i * S]);
     return nl_divf(s, (float)cur);

@@ -10,11 +10,9 @@ namespace nl {
 
 struct Affine { float a, b, c, d, e, f; };
 
-__global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ src, int sw, int sh,
-                                                      float *__restrict__ dst, int dw, int dh, Affine inv, float oob) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = blockIdx.y * blockDim.y + threadIdx.y;
-    if (col >= dw || row >= dh) return;
+// One destination pixel, exactly the reference's expression shapes.
+__device__ __forceinline__ float project_pixel(const float *__restrict__ src, int sw, int sh, const Affine &inv, int col,
+                                               int row, float oob) {
     const float x = (float)col, y = (float)row;
     // coord.go:141-145: (A*x + B*y) + C
     const float px = __fadd_rn(__fadd_rn(__fmul_rn(inv.a, x), __fmul_rn(inv.b, y)), inv.c);
@@ -32,7 +30,28 @@ __global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ 
         const float vyh = __fadd_rn(__fmul_rn(d01, ox), __fmul_rn(d11, xr));
         v = __fadd_rn(__fmul_rn(vyl, oy), __fmul_rn(vyh, yr));
     }
-    dst[(size_t)row * dw + col] = v;
+    return v;
+}
+
+// Four destination pixels of one row per thread (one 16-byte streaming store); a warp covers 128
+// consecutive destination pixels, whose 2x2 source footprints share L1 lines.
+template <bool VEC>
+__global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ src, int sw, int sh,
+                                                      float *__restrict__ dst, int dw, int dh, Affine inv, float oob) {
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y;
+    if (col >= dw || row >= dh) return;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = (col + c < dw) ? project_pixel(src, sw, sh, inv, col + c, row, oob) : 0.0f;
+    float *d = dst + (size_t)row * dw + col;
+    if (VEC) {
+        __stcs(reinterpret_cast<float4 *>(d), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (col + c < dw) d[c] = v[c];
+    }
 }
 
 }  // namespace nl
@@ -71,9 +90,11 @@ int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, fl
     NL_REQUIRE(dev_dst && (dev_src || sw == 0 || sh == 0), "NULL image pointer");
     CtxGuard g(ctx);
     Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
-    dim3 block(64, 4);
-    dim3 grid((dw + block.x - 1) / block.x, (dh + block.y - 1) / block.y);
-    project_kernel<<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
+    dim3 block(32, 8);
+    dim3 grid((dw + 4 * block.x - 1) / (4 * block.x), (dh + block.y - 1) / block.y);
+    const bool vec = (dw % 4) == 0 && (reinterpret_cast<uintptr_t>(dev_dst) % 16) == 0;
+    if (vec) project_kernel<true><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
+    else project_kernel<false><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;

@@ -78,26 +78,29 @@ __global__ void __launch_bounds__(256) stack_mean_kernel(StackArgs a) {
 }
 
 // ---- order-statistics modes ------------------------------------------------------------------
-template <int MODE, bool W> struct ColumnBufs {           // shared-memory columns per pixel
-    static constexpr int value = 1 + (W ? 1 : 0) + ((MODE == ST_WINSOR || MODE == ST_MAD) ? 1 : 0);
+// shared-memory bytes per column slot: the fp32 samples, the MAD scratch column, and (weighted
+// modes) the frame index of every sample
+template <int MODE, bool W, typename IDX> struct SlotBytes {
+    static constexpr int value = 4 * (MODE == ST_MAD ? 2 : 1) + (W ? (int)sizeof(IDX) : 0);
 };
 
-template <int MODE, bool W, int S>
+template <int MODE, bool W, int S, typename IDX>
 __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n = a.n;
     const int npad = (n + 31) & ~31;                              // clip_pass scans whole 32-slot blocks
-    constexpr int NB = ColumnBufs<MODE, W>::value;
+    constexpr int SB = SlotBytes<MODE, W, IDX>::value;
     // column element i of this lane's pixel at g[i*S]; lanes beyond a narrow tile alias a valid
     // column but never get samples (cur = 0) and never store
-    // (QW-1 rows of padding in front of the first and behind the last column buffer: the quick-select
+    // (QW-1 rows of padding in front of the first and behind the last warp region: the quick-select
     // windows may read, never use, up to QW-1 slots outside a column)
-    float *g = smem + (size_t)(QW - 1) * S + (size_t)warp * NB * S * npad + (lane % S);
-    float *gw = W ? g + (size_t)S * npad : nullptr;
-    float *sc = g + (size_t)(W ? 2 : 1) * S * npad;              // winsor / MAD scratch
-    (void)sc;
+    char *region = reinterpret_cast<char *>(smem) + (size_t)(QW - 1) * S * 4 + (size_t)warp * SB * S * npad;
+    float *g = reinterpret_cast<float *>(region) + (lane % S);
+    float *sc = g + (size_t)S * npad;                             // MAD scratch column
+    IDX *gw = reinterpret_cast<IDX *>(region + (size_t)4 * (MODE == ST_MAD ? 2 : 1) * S * npad) + (lane % S);
+    (void)sc; (void)gw;
 
     const long long tiles = (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
 #pragma unroll
                 for (int u = 0; u < 16; u++) {
                     g[cur * S] = v[u];
-                    if (W) gw[cur * S] = __ldg(a.weights + k + u);
+                    if (W) gw[cur * S] = (IDX)(k + u);
                     cur += (v[u] == v[u]) ? 1 : 0;
                 }
             }
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
                 float v = ld_stream(src + (long long)k * a.stride);
                 if (v == v) {
                     g[cur * S] = v;
-                    if (W) gw[cur * S] = __ldg(a.weights + k);
+                    if (W) gw[cur * S] = (IDX)k;
                     cur++;
                 }
             }
@@ -142,9 +145,9 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
         if (MODE == ST_MEDIAN) {
             res = qselect_median<S, (S < 32)>(g, cur);                       // stack.go:274-303
         } else if (MODE == ST_SIGMA) {
-            res = reduce_sigma<S, W>(g, gw, cur, a.sig_lo, a.sig_hi, ncl, nch);
+            res = reduce_sigma<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else if (MODE == ST_WINSOR) {
-            res = reduce_winsor<S, W>(g, gw, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+            res = reduce_winsor<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else if (MODE == ST_MAD) {
             res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else {
@@ -196,19 +199,18 @@ struct nl_stack_job {
 
 namespace nl {
 
-template <int MODE, bool W, int S>
+template <int MODE, bool W, int S, typename IDX>
 static int launch_column(nl_stack_job *job, const StackArgs &args) {
     nl_ctx *ctx = job->ctx;
-    constexpr int NB = ColumnBufs<MODE, W>::value;
-    const size_t per_warp = (size_t)NB * S * ((job->n + 31) & ~31) * sizeof(float);
-    const size_t cap = (size_t)ctx->max_smem_optin;
-    if (per_warp + (size_t)2 * (QW - 1) * S * sizeof(float) > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
-    int warps = (int)(cap / per_warp);
-    if (warps > 8) warps = 8;
+    constexpr int SB = SlotBytes<MODE, W, IDX>::value;
+    const size_t per_warp = (size_t)SB * S * ((job->n + 31) & ~31);
     const size_t pad = (size_t)2 * (QW - 1) * S * sizeof(float);
-    if (warps > 1 && per_warp * warps + pad > cap) warps--;
+    const size_t cap = (size_t)ctx->max_smem_optin;
+    if (per_warp + pad > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
+    int warps = (int)((cap - pad) / per_warp);
+    if (warps > 8) warps = 8;
     const size_t smem = per_warp * warps + pad;
-    auto kern = stack_column_kernel<MODE, W, S>;
+    auto kern = stack_column_kernel<MODE, W, S, IDX>;
     NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
     NL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem));
@@ -224,15 +226,22 @@ static int launch_column(nl_stack_job *job, const StackArgs &args) {
     return NL_OK;
 }
 
+template <int MODE, bool W, typename IDX>
+static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
+    constexpr int SB = SlotBytes<MODE, W, IDX>::value;
+    const size_t per_pixel = (size_t)SB * ((job->n + 31) & ~31);
+    const size_t pad = (size_t)2 * (QW - 1) * sizeof(float);
+    const size_t cap = (size_t)job->ctx->max_smem_optin;
+    if ((per_pixel + pad) * 32 <= cap) return launch_column<MODE, W, 32, IDX>(job, args);
+    if ((per_pixel + pad) * 8 <= cap) return launch_column<MODE, W, 8, IDX>(job, args);
+    return launch_column<MODE, W, 1, IDX>(job, args);
+}
+
 template <int MODE, bool W>
 static int launch_column_s(nl_stack_job *job, const StackArgs &args) {
-    constexpr int NB = ColumnBufs<MODE, W>::value;
-    const size_t per_pixel = (size_t)NB * ((job->n + 31) & ~31) * sizeof(float);
-    const size_t cap = (size_t)job->ctx->max_smem_optin;
-    const size_t pad = (size_t)2 * (QW - 1) * sizeof(float);
-    if ((per_pixel + pad) * 32 <= cap) return launch_column<MODE, W, 32>(job, args);
-    if ((per_pixel + pad) * 8 <= cap) return launch_column<MODE, W, 8>(job, args);
-    return launch_column<MODE, W, 1>(job, args);
+    if (!W || job->n <= 256) return launch_column_i<MODE, W, unsigned char>(job, args);
+    if (job->n <= 65536) return launch_column_i<MODE, W, unsigned short>(job, args);
+    return set_error(NL_E_INVALID, "weighted stacking of more than 65536 frames is not supported");
 }
 
 template <bool W>

@@ -11,8 +11,10 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
                           float ref_loc, float sig_lo, float sig_hi, float *res, long long *clip_lo, long long *clip_hi) {
     if (mode == ST_AUTO) mode = auto_select_mode(n);
     // clip_pass reads whole 32-slot blocks; the quick-select windows read QW-1 slots outside a column
-    std::vector<float> g_(n + 40), gw_(n + 40), wz_(n + 40), ramp(2 * (n + 2));
-    float *g = g_.data() + 4, *gw = gw_.data() + 4, *wz = wz_.data() + 4;
+    std::vector<float> g_(n + 40), wz_(n + 40), ramp(2 * (n + 2));
+    std::vector<unsigned short> gw_(n + 40);
+    float *g = g_.data() + 4, *wz = wz_.data() + 4;
+    unsigned short *gw = gw_.data() + 4;
     for (int c = 1; c <= n; c++) ramp_mean_stddev(c, ramp[2 * c], ramp[2 * c + 1]);
     long long tl = 0, th = 0;
     bool W = weights != nullptr;
@@ -35,19 +37,19 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
         for (int k = 0; k < n; k++) {
             float v = lights[k][p];
             g[cur] = v;
-            if (W) gw[cur] = weights[k];
+            if (W) gw[cur] = (unsigned short)k;
             cur += (v == v) ? 1 : 0;
         }
         if (cur == 0) { res[p] = ref_loc; continue; }
         switch (mode) {
         case ST_MEDIAN: out = qselect_median<1, true>(g, cur); break;
         case ST_SIGMA:
-            out = W ? reduce_sigma<1, true>(g, gw, cur, sig_lo, sig_hi, ncl, nch)
-                    : reduce_sigma<1, false>(g, nullptr, cur, sig_lo, sig_hi, ncl, nch);
+            out = W ? reduce_sigma<1, true, unsigned short>(g, gw, weights, cur, sig_lo, sig_hi, ncl, nch)
+                    : reduce_sigma<1, false, unsigned short>(g, nullptr, nullptr, cur, sig_lo, sig_hi, ncl, nch);
             break;
         case ST_WINSOR:
-            out = W ? reduce_winsor<1, true>(g, gw, wz, cur, sig_lo, sig_hi, ncl, nch)
-                    : reduce_winsor<1, false>(g, nullptr, wz, cur, sig_lo, sig_hi, ncl, nch);
+            out = W ? reduce_winsor<1, true, unsigned short>(g, gw, weights, cur, sig_lo, sig_hi, ncl, nch)
+                    : reduce_winsor<1, false, unsigned short>(g, nullptr, nullptr, cur, sig_lo, sig_hi, ncl, nch);
             break;
         case ST_MAD: out = reduce_mad<1>(g, wz, cur, sig_lo, sig_hi, ncl, nch); break;
         case ST_LINFIT: out = reduce_linfit<1>(g, cur, ramp.data(), sig_lo, sig_hi, ncl, nch); break;

@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Device-resident timing of every kernel on the hot path against the measured HBM roofline.
+
+    python tools/bench_kernels.py [--quick]
+
+One JSON line per kernel: achieved = ALGORITHMIC bytes per launch / CUDA-event time (DESIGN.md section 3
+states the per-unit figures), peak = MEASURED_PEAKS.json hbm_gbs.  Inputs are larger than L2 (126 MB) or
+the L2 is flushed between launches.  bench.py remains the headline benchmark; this is the per-kernel view
+the ncu captures under profiles/ are taken from.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true", help="smaller inputs (for ncu)")
+    ap.add_argument("--only", default="", help="comma list: mean,mean_w,median,sigma,sigma_w,winsor,winsor_w,mad,linfit,project,bright,incremental")
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    import nightlight_b200 as nl
+    from bench import peaks
+
+    peak, peak_src = peaks()
+    lib = nl.load_library()
+    ctx = nl.Context(0)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    only = set(x for x in args.only.split(",") if x)
+
+    def timed(fn, reps=args.reps, warm=2, flush_l2=True):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        ms = []
+        for _ in range(reps):
+            if flush_l2:
+                with torch.cuda.stream(ext):
+                    flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ext):
+                e0.record()
+            fn()
+            with torch.cuda.stream(ext):
+                e1.record()
+            ctx.sync()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms))
+
+    def report(kernel, workload, algo_bytes, ms, extra=None):
+        ach = algo_bytes / (ms * 1e-3) / 1e9
+        line = {"kernel": kernel, "workload": workload, "ms": ms, "algorithmic_bytes": algo_bytes,
+                "achieved_gbs": ach, "peak_gbs": peak, "frac": ach / peak, "peak_source": peak_src}
+        if extra:
+            line.update(extra)
+        print(json.dumps(line), flush=True)
+
+    # ---- stacking modes: 256 frames (sigma family) / 64 frames (linear fit is the heaviest) ------------
+    rows = 128 if args.quick else 512
+    width = 4096
+    w256 = (np.float32(1) / (np.float32(1) + np.float32(4) * ((np.arange(256) % 7).astype(np.float32) / np.float32(6)))).astype(np.float32)
+    stack_cases = [("mean", nl.ST_MEAN, None), ("mean_w", nl.ST_MEAN, w256), ("median", nl.ST_MEDIAN, None),
+                   ("sigma", nl.ST_SIGMA, None), ("sigma_w", nl.ST_SIGMA, w256), ("winsor", nl.ST_WINSOR_SIGMA, None),
+                   ("winsor_w", nl.ST_WINSOR_SIGMA, w256), ("mad", nl.ST_MAD_SIGMA, None), ("linfit", nl.ST_LINEAR_FIT, None)]
+    if not only or only & set(c[0] for c in stack_cases):
+        n, pixels = 256, width * rows
+        job = nl.StackJob(ctx, n, pixels)
+        job.synth_fill()
+        out = torch.empty(pixels, dtype=torch.float32, device=dev)
+        for name, mode, w in stack_cases:
+            if only and name not in only:
+                continue
+            ms = timed(lambda: job.run_dev(mode, out.data_ptr(), w, 2.75, 2.75, 0.0), flush_l2=False)
+            cl, ch = job.clip_counts()
+            report("stack<%s>" % name, "%d x %dx%d fp32, sigma 2.75/2.75 (inputs %.1f GiB > L2)" % (n, width, rows, 4.0 * n * pixels / 2**30),
+                   4.0 * (n + 1) * pixels, ms, {"mpx_in_per_s": n * pixels / ms / 1e3, "clipped": [cl, ch]})
+        job.close()
+        del out
+
+    # ---- resample: 6000x4000 -> 6000x4000, rotation 0.5 deg + shift ---------------------------------
+    if not only or "project" in only:
+        w, h = (3000, 2000) if args.quick else (6000, 4000)
+        src = torch.empty(w * h, dtype=torch.float32, device=dev)
+        dst = torch.empty(w * h, dtype=torch.float32, device=dev)
+        ctx.synth_fill(src.data_ptr(), 0, w * h, 0)
+        th = np.deg2rad(0.5)
+        trans = (C.c_float * 6)(np.cos(th), -np.sin(th), 7.25, np.sin(th), np.cos(th), -3.5)
+        ms = timed(lambda: nl.binding.check(lib.nl_project_dev(ctx.handle, C.c_void_p(src.data_ptr()), w, h, C.c_void_p(dst.data_ptr()),
+                                                               w, h, trans, float("nan"))))
+        report("project_kernel", "%dx%d -> %dx%d, rot 0.5 deg + shift, L2 flushed" % (w, h, w, h), 8.0 * w * h, ms,
+               {"mpx_per_s": w * h / ms / 1e3})
+        del src, dst
+
+    # ---- star candidate scan: 6000x4000 sky noise + 0.02 % bright pixels --------------------------------
+    if not only or "bright" in only:
+        w, h = (3000, 2000) if args.quick else (6000, 4000)
+        # sky noise around 1000 with 0.02 % bright "star" pixels
+        g = torch.Generator(device=dev).manual_seed(7)
+        img = torch.randn(w * h, dtype=torch.float32, device=dev, generator=g) * 30 + 1000
+        img += (torch.rand(w * h, device=dev, generator=g) < 2e-4).float() * 5000
+        cap = w * h // 50
+        out = np.zeros(cap, dtype=nl.STAR_DTYPE)
+        cnt = C.c_int32()
+        ms = timed(lambda: nl.binding.check(lib.nl_find_bright_dev(ctx.handle, C.c_void_p(img.data_ptr()), w * h, w, 3000.0, 16,
+                                                                   out.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))))
+        report("find_bright (2 scans + offsets + D2H of candidates)", "%dx%d, radius 16, %d candidates, L2 flushed" % (w, h, cnt.value),
+               4.0 * w * h, ms, {"mpx_per_s": w * h / ms / 1e3, "note": "whole call incl. host sync; the image is read twice (count, write)"})
+        del img
+
+    # ---- stack-of-stacks accumulate -----------------------------------------------------------------
+    if not only or "incremental" in only:
+        px = 4096 * (1024 if args.quick else 4096)
+        acc = torch.zeros(px, dtype=torch.float32, device=dev)
+        light = torch.ones(px, dtype=torch.float32, device=dev)
+        ms = timed(lambda: nl.binding.check(lib.nl_stack_incremental_dev(ctx.handle, C.c_void_p(acc.data_ptr()), C.c_void_p(light.data_ptr()),
+                                                                         px, 3.0, 0)))
+        report("incremental_kernel", "%d px acc += light*w, L2 flushed" % px, 12.0 * px, ms)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
