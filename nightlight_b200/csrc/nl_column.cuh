@@ -460,6 +460,7 @@ template <int S>
 NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
     float median = qselect_median<S, (S < 32)>(g, cur);
     for (int i = 0; i < cur; i++) ad[i * S] = fabsf(nl_subf(g[i * S], median));
+    if (cur == 0 && S == 32) ad[0] = 0.0f;         // an ungated parked lane compares slot 0 with itself: never a NaN
     float mad = qselect_median<S, (S < 32)>(ad, cur);
     float sd = nl_mulf(mad, 1.4826f);
     float lo = nl_subf(median, nl_mulf(sig_lo, sd));

@@ -105,26 +105,36 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
     const long long tiles = (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
 
-    for (;;) {
-        // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if ((long long)t >= tiles) break;
-        const long long p = (long long)t * S + lane;
+    // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles from a
+    // counter -- one tile ahead, so that the next tile's 128-byte row segments (one per frame) can be
+    // prefetched into L2 while this tile is being reduced (~100 us later the gather finds them there)
+    auto next_tile = [&]() {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(a.tile_counter, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    long long t = next_tile();
+    while (t < tiles) {
+        const long long tn = next_tile();
+        if (tn < tiles) {
+            const float *nsrc = a.frames + tn * S;
+            for (int k = lane; k < n; k += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (long long)k * a.stride));
+        }
+        const long long p = t * S + lane;
         const bool valid = lane < S && p < a.pixels;
         int cur = 0;
         if (valid) {
-            // gather the non-NaN samples of pixel p in frame order (stack.go:380-387): 16 loads
+            // gather the non-NaN samples of pixel p in frame order (stack.go:380-387): 32 loads
             // in flight per lane, each a 128-byte row segment per warp
             const float *src = a.frames + p;
             int k = 0;
-            for (; k + 16 <= n; k += 16) {
-                float v[16];
+            for (; k + 32 <= n; k += 32) {
+                float v[32];
 #pragma unroll
-                for (int u = 0; u < 16; u++) v[u] = ld_stream(src + (long long)(k + u) * a.stride);
+                for (int u = 0; u < 32; u++) v[u] = ld_stream(src + (long long)(k + u) * a.stride);
 #pragma unroll
-                for (int u = 0; u < 16; u++) {
+                for (int u = 0; u < 32; u++) {
                     g[cur * S] = v[u];
                     if (W) gw[cur * S] = (IDX)(k + u);
                     cur += (v[u] == v[u]) ? 1 : 0;
@@ -155,6 +165,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
         }
         if (valid) a.out[p] = cur == 0 ? a.ref_loc : res;         // stack.go:388-397
         __syncwarp();
+        t = tn;
     }
     if (MODE >= ST_SIGMA) {
         // clip totals (stack.go:193-198): warp reduce, one atomic pair per warp
