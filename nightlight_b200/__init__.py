@@ -13,6 +13,7 @@ from .binding import (  # noqa: F401
     ST_MEDIAN, ST_MEAN, ST_SIGMA, ST_WINSOR_SIGMA, ST_MAD_SIGMA, ST_LINEAR_FIT, ST_AUTO,
     W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR, DECLARED_SYMBOLS,
 )
-from .ops import OpStack, OpStackBatches, project, transform_invert, find_bright_pixels, find_stars, get_weights  # noqa: F401
+from .ops import (OpStack, OpStackBatches, project, transform_invert, find_bright_pixels, find_stars, get_weights,  # noqa: F401
+                  find_sigmas_and_stack)
 
 __version__ = "0.1.0"

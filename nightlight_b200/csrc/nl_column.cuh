@@ -144,7 +144,25 @@ struct ColMem {
 // 0 there for an empty column).  GATE adds an explicit `active` term for lanes that alias another
 // lane's column (narrow tiles).
 // ---------------------------------------------------------------------------------------------
-constexpr int QW = 4;
+#ifndef NL_QW
+#define NL_QW 4
+#endif
+constexpr int QW = NL_QW;           // samples per scan window
+
+template <typename M, int N, int DIR, int J = 0>
+struct WindowLoader {
+    static NL_HD void run(typename M::pos_t p, float *w) {
+        w[J] = M::template ld<DIR * J>(p);
+        WindowLoader<M, N, DIR, J + 1>::run(p, w);
+    }
+};
+template <typename M, int N, int DIR>
+struct WindowLoader<M, N, DIR, N> {
+    static NL_HD void run(typename M::pos_t, float *) {}
+};
+template <typename M, int N, int DIR>
+NL_HD void load_window(typename M::pos_t p, float *w) { WindowLoader<M, N, DIR>::run(p, w); }
+
 #ifndef NL_QSTEPS
 #define NL_QSTEPS 4
 #endif
@@ -162,19 +180,20 @@ NL_HD float qselect(float *a, int n, int k) {
     while (any_active) {
 #pragma unroll
         for (int u = 0; u < QSTEPS; u++) {
-            const float l0 = M::template ld<0>(l), l1 = M::template ld<1>(l), l2 = M::template ld<2>(l), l3 = M::template ld<3>(l);
-            const float r0 = M::template ld<0>(r), r1 = M::template ld<-1>(r), r2 = M::template ld<-2>(r), r3 = M::template ld<-3>(r);
-            const bool sl = l0 >= pivot;                     // left scan stops here  (qsort.go:104-108)
-            const bool sr = r0 <= pivot;                     // right scan stops here (qsort.go:109-113)
-            int tl = (l3 >= pivot) ? 3 : 4;                  // first stop among the window slots 1..3
-            tl = (l2 >= pivot) ? 2 : tl;
-            tl = (l1 >= pivot) ? 1 : tl;
-            int tr = (r3 <= pivot) ? 3 : 4;
-            tr = (r2 <= pivot) ? 2 : tr;
-            tr = (r1 <= pivot) ? 1 : tr;
+            float lw[QW], rw[QW];                            // the two windows
+            load_window<M, QW, 1>(l, lw);
+            load_window<M, QW, -1>(r, rw);
+            const bool sl = lw[0] >= pivot;                  // left scan stops here  (qsort.go:104-108)
+            const bool sr = rw[0] <= pivot;                  // right scan stops here (qsort.go:109-113)
+            int tl = QW, tr = QW;                            // first stop among the window slots 1..QW-1
+#pragma unroll
+            for (int j = QW - 1; j >= 1; j--) {
+                tl = (lw[j] >= pivot) ? j : tl;
+                tr = (rw[j] <= pivot) ? j : tr;
+            }
             const int d = M::diff(r, l);
             const bool sw = sl & sr & (d > 0);               // both stopped, not crossed: swap (qsort.go:114-115)
-            if (sw) { M::st(l, r0); M::st(r, l0); }
+            if (sw) { M::st(l, rw[0]); M::st(r, lw[0]); }
             const bool near = d < QW;                        // the windows saw slots the swap has just changed
             const int step = (sw & near) ? 1 : 0;
             int dl = (!sl | sw) ? (step ? 1 : tl) : 0;
@@ -331,52 +350,31 @@ NL_HD float winsor_sigma(const float *g, int cur, float median, float sd) {
 }
 
 // In-place ascending sort of a column.  The reference sorts with its Hoare quicksort
-// (qsort.go:26-32); the sorted array is unique, so any correct sort is bit-exact.  Heap sort:
-// no recursion, no stack, O(n log n) for every input.
+// (qsort.go:26-32); the sorted array is unique, so any correct sort is bit-exact.  SIMT form: a
+// bitonic sorting network in its ascending-only formulation (every compare-exchange puts the
+// smaller sample at the lower index: the first stage of each merge mirrors the upper half instead
+// of sorting it downwards), which makes slots at or beyond n behave like +infinity without being
+// stored: an exchange whose upper slot is >= n is skipped.  The network is data independent, so the
+// 32 lanes (32 columns of different length n <= nmax) run it in lock step without divergence.
+// nmax: the longest column of the warp (host: n).
 template <int S>
-NL_HD void sort_column(float *a, int n) {
-    if (n < 2) return;
-    for (int start = (n >> 1) - 1; start >= 0; start--) {      // heapify
-        int root = start;
-        float v = a[root * S];
-        for (;;) {
-            int child = 2 * root + 1;
-            if (child >= n) break;
-            float c = a[child * S];
-            if (child + 1 < n) { float c2 = a[(child + 1) * S]; if (c2 > c) { c = c2; child++; } }
-            if (c <= v) break;
-            a[root * S] = c;
-            root = child;
+NL_HD void sort_column(float *a, int n, int nmax) {
+    int P = 1;
+    while (P < nmax) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int s = k >> 1; s >= 1; s >>= 1) {
+            const bool mirror = s == (k >> 1);
+#pragma unroll 4
+            for (int i = 0; i < (P >> 1); i++) {
+                const int lo = ((i & ~(s - 1)) << 1) | (i & (s - 1));
+                const int hi = mirror ? (lo ^ (k - 1)) : (lo | s);
+                if (hi < n) {
+                    const float x = a[lo * S], y = a[hi * S];
+                    a[lo * S] = y < x ? y : x;
+                    a[hi * S] = y < x ? x : y;
+                }
+            }
         }
-        a[root * S] = v;
-    }
-    for (int end = n - 1; end > 0; end--) {
-        float v = a[end * S];
-        a[end * S] = a[0];
-        int root = 0;
-        for (;;) {
-            int child = 2 * root + 1;
-            if (child >= end) break;
-            float c = a[child * S];
-            if (child + 1 < end) { float c2 = a[(child + 1) * S]; if (c2 > c) { c = c2; child++; } }
-            if (c <= v) break;
-            a[root * S] = c;
-            root = child;
-        }
-        a[root * S] = v;
-    }
-}
-
-// Insertion sort: used for the re-sorts of StackLinearFit, where the array is sorted except for
-// the few slots the rejection pass overwrote.
-template <int S>
-NL_HD void insertion_sort_column(float *a, int n) {
-    for (int i = 1; i < n; i++) {
-        float v = a[i * S];
-        int j = i - 1;
-        if (a[j * S] <= v) continue;
-        while (j >= 0 && a[j * S] > v) { a[(j + 1) * S] = a[j * S]; j--; }
-        a[(j + 1) * S] = v;
     }
 }
 
@@ -473,42 +471,55 @@ NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi,
 
 // stack.go:834-918 StackLinearFit.  ramp[2*c], ramp[2*c+1] = MeanStdDev of 0..c-1 (precomputed per
 // length by ramp_mean_stddev; the reference recomputes it per pixel, stats.go:570).
+// The reference rejects a sample by overwriting its slot with the current front sample and then
+// drops the front slots (stack.go:889-909), and sorts again.  Every surviving value ends up in the
+// slice exactly once, so the next round's SORTED array is the current sorted array with the rejected
+// slots removed -- a stable compaction, no second sort.  All 32 lanes call this together (nmax = the
+// longest column of the warp); cur may be 0.
 template <int S>
-NL_HD float reduce_linfit(float *g, int cur, const float *ramp, float sig_lo, float sig_hi, int &ncl, int &nch) {
+NL_HD float reduce_linfit(float *g, int cur, int nmax, const float *ramp, float sig_lo, float sig_hi, int &ncl, int &nch) {
+    sort_column<S>(g, cur, nmax);
     float mean = 0.0f;
-    bool first = true;
-    for (;;) {
-        if (first) sort_column<S>(g, cur); else insertion_sort_column<S>(g, cur);
-        first = false;
+    bool done = cur == 0;
+    while (NL_ANY(!done)) {
+        const int m = done ? 0 : cur;
         // LinearRegression(xs, ys), stats.go:569-586
-        float xm = ramp[2 * cur], xsd = ramp[2 * cur + 1];
-        float ysd;
-        mean_stddev<S>(g, cur, mean, ysd);
+        const float xm = ramp[2 * m], xsd = ramp[2 * m + 1];
+        float ym, ysd;
+        mean_stddev<S>(g, m, ym, ysd);
         float corr = 0.0f;
-        for (int i = 0; i < cur; i++)
-            corr = nl_addf(corr, nl_mulf(nl_subf((float)i, xm), nl_subf(g[i * S], mean)));
-        corr = nl_divf(corr, nl_mulf(nl_mulf(xsd, ysd), nl_addf((float)cur, 1.0f)));
-        float slope = nl_divf(nl_mulf(corr, ysd), xsd);
-        float icpt = nl_subf(mean, nl_mulf(slope, xm));
+#pragma unroll 4
+        for (int i = 0; i < m; i++)
+            corr = nl_addf(corr, nl_mulf(nl_subf((float)i, xm), nl_subf(g[i * S], ym)));
+        corr = nl_divf(corr, nl_mulf(nl_mulf(xsd, ysd), nl_addf((float)m, 1.0f)));
+        const float slope = nl_divf(nl_mulf(corr, ysd), xsd);
+        const float icpt = nl_subf(ym, nl_mulf(slope, xm));
         // mean absolute residual, stack.go:878-886
         float sigma = 0.0f;
-        for (int i = 0; i < cur; i++) {
-            float lin = nl_addf(nl_mulf((float)i, slope), icpt);
+#pragma unroll 4
+        for (int i = 0; i < m; i++) {
+            const float lin = nl_addf(nl_mulf((float)i, slope), icpt);
             sigma = nl_addf(sigma, fabsf(nl_subf(g[i * S], lin)));
         }
-        sigma = nl_divf(sigma, (float)cur);
-        // rejection: overwrite from the front, stack.go:889-909
-        int left = 0;
-        float lob = nl_mulf(sig_lo, sigma), hib = nl_mulf(sig_hi, sigma);
-        for (int i = 0; i < cur; i++) {
-            float v = g[i * S];
-            float lin = nl_addf(nl_mulf((float)i, slope), icpt);
-            if (nl_subf(lin, v) > lob) { g[i * S] = g[left * S]; left++; ncl++; }
-            else if (nl_subf(v, lin) > hib) { g[i * S] = g[left * S]; left++; nch++; }
+        sigma = nl_divf(sigma, (float)m);
+        // rejection (stack.go:889-909) fused with the compaction of the survivors
+        int w = 0;
+        const float lob = nl_mulf(sig_lo, sigma), hib = nl_mulf(sig_hi, sigma);
+#pragma unroll 4
+        for (int i = 0; i < m; i++) {
+            const float v = g[i * S];
+            const float lin = nl_addf(nl_mulf((float)i, slope), icpt);
+            const bool low = nl_subf(lin, v) > lob;
+            const bool high = !low && nl_subf(v, lin) > hib;
+            ncl += low ? 1 : 0;
+            nch += high ? 1 : 0;
+            if (!(low | high)) { g[w * S] = v; w++; }
         }
-        if (left == 0 || cur < 3) break;
-        g += left * S;
-        cur -= left;
+        if (!done) {
+            mean = ym;
+            if (w == cur || cur < 3) done = true;          // left == 0 || len < 3
+            cur = w;
+        }
     }
     return mean;
 }

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
         } else if (MODE == ST_MAD) {
             res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else {
-            res = cur > 0 ? reduce_linfit<S>(g, cur, a.ramp, a.sig_lo, a.sig_hi, ncl, nch) : 0.0f;
+            res = reduce_linfit<S>(g, cur, __reduce_max_sync(0xffffffffu, cur), a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
         }
         if (valid) a.out[p] = cur == 0 ? a.ref_loc : res;         // stack.go:388-397
         __syncwarp();

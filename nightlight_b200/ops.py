@@ -163,3 +163,72 @@ def find_stars(ctx: B.Context, data, width, location, scale, starSig, bpSigma, s
                                        starSig, bpSigma, starInOut, radius, medianDiffStdDev,
                                        out.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(sos), C.byref(hfr)))
     return out[:min(n.value, cap)], np.float32(sos.value), np.float32(hfr.value)
+
+
+def find_sigmas_and_stack(stack_fn, mode, n_frames, pixels, clip_perc_low, clip_perc_high, log=None):
+    """Goal-seek of the clipping sigmas for target clip percentages, restated from the reference's
+    DEAD code (internal/ops/stack/stackfindsigma.go:27-170 is inside a comment block; nothing calls it,
+    so parity is unpinned by the reference).  `stack_fn(sigma_low, sigma_high)` runs one stack and returns
+    (result, clipLow, clipHigh): StackJob.run keeps the frames resident in HBM, so the up to 20 trial
+    stacks cost no re-upload.  Host arithmetic is float32 like the Go code.
+    -> (result, clipLow, clipHigh, sigmaLow, sigmaHigh)"""
+    f32 = np.float32
+    say = log or (lambda *_: None)
+    if mode == B.ST_AUTO:                                   # :29-32
+        mode = load_library().nl_auto_select_mode(int(n_frames))
+    total = f32(pixels * n_frames)
+    lo_t, hi_t = f32(clip_perc_low), f32(clip_perc_high)
+
+    def perc(c):
+        return f32(f32(f32(c) * f32(100.0)) / total)
+
+    if mode in (B.ST_WINSOR_SIGMA, B.ST_SIGMA):             # binarySearchAndStack, :48-98
+        low_l, low_r, high_l, high_r = f32(1.0), f32(11.0), f32(1.0), f32(11.0)
+        low_m, high_m = f32(0.5) * f32(low_l + low_r), f32(0.5) * f32(high_l + high_r)
+        i = 0
+        while True:
+            say("Step %d: stSigLow %.2f stSigHigh %.2f" % (i, low_m, high_m))
+            res, cl, ch = stack_fn(float(low_m), float(high_m))
+            dl = int(f32(f32(100) * perc(cl)) + f32(0.5)) - int(f32(100) * lo_t)
+            dh = int(f32(f32(100) * perc(ch)) + f32(0.5)) - int(f32(100) * hi_t)
+            if (dl == 0 and dh == 0) or i >= 20:
+                return res, cl, ch, float(low_m), float(high_m)
+            if dl > 0:
+                low_l = low_m
+            elif dl < 0:
+                low_r = low_m
+            if dl != 0:
+                low_m = f32(0.5) * f32(low_l + low_r)
+            if dh > 0:
+                high_l = high_m
+            elif dh < 0:
+                high_r = high_m
+            if dh != 0:
+                high_m = f32(0.5) * f32(high_l + high_r)
+            i += 1
+    if mode == B.ST_LINEAR_FIT:                             # newtonMethodAndStack, :101-170
+        sig_lo, sig_hi, eps = f32(6.0), f32(6.0), f32(0.005)
+        i = 0
+        while True:
+            say("Step %d: stSigLow %.2f stSigHigh %.2f" % (i, sig_lo, sig_hi))
+            res, cl, ch = stack_fn(float(sig_lo), float(sig_hi))
+            d_l = f32(perc(cl) - lo_t)
+            d_h = f32(perc(ch) - lo_t)                      # the reference uses the LOW target here too (:114)
+            if (int(f32(100) * d_l + f32(0.5)) == 0 and int(f32(100) * d_h + f32(0.5)) == 0) or i >= 20:
+                return res, cl, ch, float(sig_lo), float(sig_hi)
+            i += 1
+            _, cl2, _ = stack_fn(float(f32(sig_lo + eps)), float(sig_hi))
+            diff_l = f32(f32(f32(perc(cl2) - lo_t) - d_l) / eps)
+            if diff_l == 0:
+                return res, cl, ch, float(sig_lo), float(sig_hi)
+            new_lo = min(max(f32(sig_lo - f32(d_l / diff_l)), f32(0.1)), f32(20))
+            i += 1
+            _, _, ch3 = stack_fn(float(sig_lo), float(f32(sig_hi + eps)))
+            diff_h = f32(f32(f32(perc(ch3) - lo_t) - d_h) / eps)   # :155 again the low target
+            if diff_h == 0:
+                return res, cl, ch, float(sig_lo), float(sig_hi)
+            new_hi = min(max(f32(sig_hi - f32(d_h / diff_h)), f32(0.1)), f32(20))
+            sig_lo, sig_hi = new_lo, new_hi
+            i += 1
+    res, cl, ch = stack_fn(0.0, 0.0)                        # :41-44: mode has no sigmas
+    return res, cl, ch, 0.0, 0.0

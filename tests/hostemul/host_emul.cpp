@@ -52,7 +52,7 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
                     : reduce_winsor<1, false, unsigned short>(g, nullptr, nullptr, cur, sig_lo, sig_hi, ncl, nch);
             break;
         case ST_MAD: out = reduce_mad<1>(g, wz, cur, sig_lo, sig_hi, ncl, nch); break;
-        case ST_LINFIT: out = reduce_linfit<1>(g, cur, ramp.data(), sig_lo, sig_hi, ncl, nch); break;
+        case ST_LINFIT: out = reduce_linfit<1>(g, cur, cur, ramp.data(), sig_lo, sig_hi, ncl, nch); break;
         default: return -1;
         }
         res[p] = out;
@@ -70,4 +70,4 @@ extern "C" float emul_qselect_median(float *a, int n) {
     for (int i = 0; i < n; i++) a[i] = b[4 + i];
     return m;
 }
-extern "C" void emul_sort(float *a, int n, int insertion) { if (insertion) insertion_sort_column<1>(a, n); else sort_column<1>(a, n); }
+extern "C" void emul_sort(float *a, int n, int nmax) { sort_column<1>(a, n, nmax > n ? nmax : n); }

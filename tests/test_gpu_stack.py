@@ -185,3 +185,19 @@ def test_full_size_sampled_tiles(ctx, mode, weighted, n, pixels):
         assert 0.005 < frac < 0.5, frac
     # size-independent property: every stacked value lies within the range of the synthetic samples
     assert res.min() >= 1024 - 256 - 512 and res.max() <= 1024 + 256 + 4096
+
+
+def test_goal_seek_matches_oracle_driven_search(ctx):
+    """a21: the restated sigma goal-seek around a resident StackJob follows the same trajectory as the
+    same host logic driven by the oracle (identical clip counts at every step)"""
+    frames = O.synth_frames(40, 5000, 4000)
+    n, p = frames.shape
+    with nl.StackJob(ctx, n, p) as job:
+        for i in range(n):
+            job.put_frame(i, frames[i])
+        for mode, name, lo, hi in ((nl.ST_SIGMA, "sigma", 1.0, 1.5), (nl.ST_WINSOR_SIGMA, "winsor", 0.5, 2.0),
+                                   (nl.ST_AUTO, "linfit", 2.0, 2.0)):
+            got = nl.find_sigmas_and_stack(lambda sl, sh: job.run(mode, None, sl, sh), mode, n, p, lo, hi)
+            want = nl.find_sigmas_and_stack(lambda sl, sh: O.stack(frames, name, sl, sh), mode, n, p, lo, hi)
+            assert got[1:] == want[1:], (name, got[1:], want[1:])
+            assert bits_equal(got[0], want[0]), (name, first_mismatch(got[0], want[0]))

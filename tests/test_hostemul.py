@@ -48,13 +48,15 @@ def test_qselect_permutation(hostemul):
 
 
 def test_sorts(hostemul):
+    """the bitonic network with virtual +inf padding, for every length and a longer warp maximum"""
     rng = np.random.default_rng(3)
-    for n in (1, 2, 3, 17, 64, 255, 256, 1000):
-        a = rng.standard_normal(n).astype(np.float32)
-        for ins in (0, 1):
-            b = a.copy()
-            hostemul.emul_sort(b.ctypes.data_as(fp), n, ins)
-            assert np.array_equal(b, np.sort(a))
+    for n in list(range(1, 40)) + [63, 64, 65, 100, 255, 256, 257, 1000]:
+        for kind in range(2):
+            a = rng.standard_normal(n).astype(np.float32) if kind == 0 else rng.integers(0, 4, n).astype(np.float32)
+            for nmax in (n, n + 37):
+                b = a.copy()
+                hostemul.emul_sort(b.ctypes.data_as(fp), n, nmax)
+                assert np.array_equal(b, np.sort(a)), (n, kind, nmax)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 16, 25, 64, 256])

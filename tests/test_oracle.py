@@ -107,3 +107,28 @@ def test_synth_matches_python_generator():
     got = O.synth_frame(123456, 64, 9)
     want = np.array([pyref.synth_sample(123456 + i, 9) for i in range(64)], dtype=np.float32)
     assert bits_equal(got, want)
+
+
+def test_goal_seek_host_logic_on_the_oracle():
+    """find_sigmas_and_stack (restated dead code, parity unpinned) driven by the oracle: the binary
+    search reaches the requested clip percentages, the Newton variant terminates within its 20 steps"""
+    import nightlight_b200 as nl
+    frames = O.synth_frames(32, 1000, 3000)
+    n, p = frames.shape
+    steps = []
+
+    def stack_fn(mode):
+        def fn(sl, sh):
+            steps.append((sl, sh))
+            return O.stack(frames, mode, sl, sh)
+        return fn
+    res, cl, ch, sl, sh = nl.find_sigmas_and_stack(stack_fn("sigma"), nl.ST_SIGMA, n, p, 1.0, 1.5)
+    assert int(100 * (cl * 100.0 / (n * p)) + 0.5) == 100 and int(100 * (ch * 100.0 / (n * p)) + 0.5) == 150
+    assert 1.0 <= sl <= 11.0 and 1.0 <= sh <= 11.0 and len(steps) <= 21
+    want = O.stack(frames, "sigma", sl, sh)
+    assert np.array_equal(res.view(np.uint32), want[0].view(np.uint32)) and (cl, ch) == want[1:]
+    steps.clear()
+    res, cl, ch, sl, sh = nl.find_sigmas_and_stack(stack_fn("linfit"), nl.ST_AUTO, n, p, 2.0, 2.0)   # 32 frames -> linear fit
+    assert len(steps) <= 23 and 0.1 <= sl <= 20 and 0.1 <= sh <= 20
+    res2, cl2, ch2, _, _ = nl.find_sigmas_and_stack(stack_fn("median"), nl.ST_MEDIAN, n, p, 1.0, 1.0)
+    assert (cl2, ch2) == (0, 0)
