@@ -93,3 +93,35 @@ def test_find_stars_matches_oracle(ctx, w, h):
         assert len(got[0]) == len(want[0]) and len(got[0]) > 10
         assert got[0].tobytes() == want[0].tobytes()
         assert bits_equal([got[1], got[2]], [want[1], want[2]])
+
+
+def test_config3_pipeline_detect_project_stack(ctx):
+    """BASELINE config 3 in miniature: star-detect every frame, resample it with its (given) alignment
+    transform, stack the aligned frames -- CUDA path against the oracle at every stage.  The triangle
+    matcher that produces the transform stays on the host in Go (gonum Nelder-Mead, parity unpinned), so
+    the transforms are inputs here."""
+    from util import MODE_ID
+    w, h, n = 320, 240, 8
+    base = star_field(w, h, 40, seed=5, noise=2.0, hot=0).reshape(h, w)
+    rng = np.random.default_rng(9)
+    aligned_gpu, aligned_cpu = [], []
+    for k in range(n):
+        th = np.deg2rad(rng.uniform(-1, 1))
+        trans = np.array([np.cos(th), -np.sin(th), rng.uniform(-6, 6), np.sin(th), np.cos(th), rng.uniform(-6, 6)], np.float32)
+        frame = (base + rng.standard_normal((h, w)).astype(np.float32) * 2).astype(np.float32).reshape(-1)
+        sg = nl.find_stars(ctx, frame, w, 100.0, 2.0, 15.0, 0.0, 1.4, 8, 0.0)
+        sc = O.find_stars(frame, w, 100.0, 2.0, 15.0, 0.0, 1.4, 8, 0.0)
+        assert sg[0].tobytes() == sc[0].tobytes() and len(sg[0]) > 5
+        aligned_gpu.append(nl.project(ctx, frame, w, h, w, h, trans))          # NaN outside the source
+        aligned_cpu.append(O.project(frame, w, h, w, h, trans, np.float32(np.nan)))
+        assert bits_equal(aligned_gpu[-1], aligned_cpu[-1])
+    fg, fc = np.stack(aligned_gpu), np.stack(aligned_cpu)
+    assert np.isnan(fg).any()
+    for mode in ("sigma", "winsor", "median"):
+        with nl.StackJob(ctx, n, w * h) as job:
+            for i in range(n):
+                job.put_frame(i, fg[i])
+            got = job.run(MODE_ID[mode])
+        want = O.stack(fc, mode)
+        assert bits_equal(got[0], want[0]), (mode, first_mismatch(got[0], want[0]))
+        assert got[1:] == want[1:]
