@@ -33,25 +33,21 @@ __device__ __forceinline__ float project_pixel(const float *__restrict__ src, in
     return v;
 }
 
-// Four destination pixels of one row per thread (one 16-byte streaming store); a warp covers 128
-// consecutive destination pixels, whose 2x2 source footprints share L1 lines.
-template <bool VEC>
+// One destination column x four rows per thread: the 32 lanes of a warp cover 32 consecutive
+// destination pixels of a row, so every one of the 16 gathers of a thread is a (nearly) contiguous
+// 128-byte warp access and every store a full 128-byte line; the four rows give each thread 16
+// independent loads in flight and their 2x2 footprints share L1 lines with the rows above and below.
 __global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ src, int sw, int sh,
                                                       float *__restrict__ dst, int dw, int dh, Affine inv, float oob) {
-    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int row = blockIdx.y * blockDim.y + threadIdx.y;
-    if (col >= dw || row >= dh) return;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
+    if (col >= dw || row0 >= dh) return;
     float v[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) v[c] = (col + c < dw) ? project_pixel(src, sw, sh, inv, col + c, row, oob) : 0.0f;
-    float *d = dst + (size_t)row * dw + col;
-    if (VEC) {
-        __stcs(reinterpret_cast<float4 *>(d), make_float4(v[0], v[1], v[2], v[3]));
-    } else {
+    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel(src, sw, sh, inv, col, row0 + r, oob) : 0.0f;
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (col + c < dw) d[c] = v[c];
-    }
+    for (int r = 0; r < 4; r++)
+        if (row0 + r < dh) __stcs(dst + (size_t)(row0 + r) * dw + col, v[r]);
 }
 
 }  // namespace nl
@@ -90,11 +86,9 @@ int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, fl
     NL_REQUIRE(dev_dst && (dev_src || sw == 0 || sh == 0), "NULL image pointer");
     CtxGuard g(ctx);
     Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
-    dim3 block(32, 8);
-    dim3 grid((dw + 4 * block.x - 1) / (4 * block.x), (dh + block.y - 1) / block.y);
-    const bool vec = (dw % 4) == 0 && (reinterpret_cast<uintptr_t>(dev_dst) % 16) == 0;
-    if (vec) project_kernel<true><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
-    else project_kernel<false><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
+    dim3 block(64, 4);
+    dim3 grid((dw + block.x - 1) / block.x, (dh + 4 * block.y - 1) / (4 * block.y));
+    project_kernel<<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;
