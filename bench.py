@@ -187,8 +187,32 @@ def run_b200(args):
     ctx.sync()
     out = torch.empty(pixels, dtype=torch.float32, device="cuda")
     gathered = torch.empty(pixels * world, dtype=torch.float32, device="cuda") if world > 1 else None
+    # Multi-GPU reassembly of the stacked image: fused into the stack kernel's epilogue (every result is
+    # also stored into the peer-mapped gathered image of every other rank over NVLink), with one tiny
+    # all-reduce as the "everybody's stores have landed" signal.  --gather nccl keeps the plain
+    # all_gather_into_tensor of the stripes; the fused path is verified against it once before timing.
+    peer = None
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda") if world > 1 else None
+    if world > 1 and args.gather == "peer":
+        from nightlight_b200.stripes import PeerGather
+        try:
+            peer = PeerGather(ctx, pixels)
+        except Exception as e:                       # no peer access on this box: say so and fall back
+            if rank == 0:
+                print("peer mapping unavailable (%s), using the NCCL all-gather" % e, file=sys.stderr)
+            peer = None
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and peer is not None:
+            peer.close()
+            peer = None
 
     def step():
+        if peer is not None:
+            job.run_dev_bcast(nl.ST_SIGMA, peer.local_out, peer.peer_outs, None, SIG_LO, SIG_HI, 0.0)
+            with torch.cuda.stream(ext):
+                dist.all_reduce(flag)
+            return
         job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, SIG_LO, SIG_HI, 0.0)
         if world > 1:
             with torch.cuda.stream(ext):
@@ -204,6 +228,22 @@ def run_b200(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    gather_desc = "none (1 GPU)"
+    if world > 1:
+        gather_desc = "NCCL all_gather_into_tensor of the stripes"
+    if peer is not None:
+        # verify the fused reassembly against NCCL once
+        job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, SIG_LO, SIG_HI, 0.0)
+        with torch.cuda.stream(ext):
+            dist.all_gather_into_tensor(gathered, out)
+        barrier()
+        same = bool(np.array_equal(peer.to_host().view(np.uint32), gathered.cpu().numpy().view(np.uint32)))
+        agree = torch.tensor([1 if same else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) != 1:
+            raise SystemExit("fused peer-store reassembly differs from the NCCL all-gather")
+        gather_desc = "fused: stack kernel epilogue stores every stripe into all peers' images (CUDA IPC over NVLink), verified against NCCL all_gather"
+        barrier()
 
     # ---- timed region: K steps, device-resident frames (16 GiB per GPU >> 126 MB L2: no flush needed)
     sampler = ClockSampler(local_rank)
@@ -215,10 +255,15 @@ def run_b200(args):
     for i in range(args.steps):
         with torch.cuda.stream(ext):
             ev[2 + 2 * i].record()
-        job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, SIG_LO, SIG_HI, 0.0)
+        if peer is not None:
+            job.run_dev_bcast(nl.ST_SIGMA, peer.local_out, peer.peer_outs, None, SIG_LO, SIG_HI, 0.0)
+        else:
+            job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, SIG_LO, SIG_HI, 0.0)
         with torch.cuda.stream(ext):
             ev[3 + 2 * i].record()
-            if world > 1:
+            if peer is not None:
+                dist.all_reduce(flag)
+            elif world > 1:
                 dist.all_gather_into_tensor(gathered, out)
     with torch.cuda.stream(ext):
         ev[1].record()
@@ -274,13 +319,15 @@ def run_b200(args):
             "config": {"workload": "sigma-clip stack 2.75/2.75 of 256 x 4096x%d fp32 frames per GPU (row stripe of a "
                                    "4096x%d image), frames resident in HBM" % (rows, rows * world),
                        "n_frames": N_FRAMES, "width": WIDTH, "rows_per_gpu": rows, "mode": "sigma", "sigma": [SIG_LO, SIG_HI],
-                       "parallelism": "row stripes x%d, all-gather of the stacked image" % world,
+                       "parallelism": "row stripes x%d" % world, "gather": gather_desc,
                        "l2": "inputs (%.1f GiB per GPU) larger than L2, no flush" % (4.0 * N_FRAMES * pixels / 2**30),
                        "mpx_out_per_s": world * pixels / (ms_per_step * 1e-3) / 1e6,
                        "clipped": [clip_low, clip_high]},
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches,
         }
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     job.close()
     ctx.close()
     if world > 1:
@@ -382,6 +429,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-stripes", type=int, default=8, help="row stripes of the pipelined end-to-end pass")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="multi-GPU reassembly of the stacked image")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

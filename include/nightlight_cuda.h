@@ -82,6 +82,13 @@ int  nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float s
  * the clip counters are readable after nl_ctx_sync via nl_stack_clip_counts. */
 int  nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                       float ref_frame_loc, float *dev_out);
+/* Same, and the result is ALSO stored to n_peers (<= 8) further device buffers of `pixels` floats each:
+ * multi-GPU row stripes pass, for every other rank, the address of this rank's stripe inside that
+ * rank's gathered image (peer memory mapped with nl_ipc_open_handle), which fuses the reassembly of the
+ * stacked image (the reference is single-process and has no counterpart) into the
+ * kernel's epilogue instead of running an all-gather afterwards. */
+int  nl_stack_run_dev_bcast(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                            float ref_frame_loc, float *dev_out, float *const *peer_outs, int32_t n_peers);
 int  nl_stack_clip_counts(nl_stack_job *job, int64_t *clip_low, int64_t *clip_high);
 int  nl_stack_end(nl_stack_job *job);
 /* autoSelectStackingMode (stack.go:45-55) */
@@ -123,6 +130,10 @@ int  nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64_t count, 
 /* ---- plain device memory helpers for bindings without a CUDA runtime of their own --------- */
 int  nl_dev_alloc(nl_ctx *ctx, int64_t bytes, void **dev);
 int  nl_dev_free(nl_ctx *ctx, void *dev);
+/* cross-process peer mapping of a buffer from nl_dev_alloc (CUDA IPC, one process per GPU) */
+int  nl_ipc_get_handle(nl_ctx *ctx, void *dev, unsigned char handle[64]);
+int  nl_ipc_open_handle(nl_ctx *ctx, const unsigned char handle[64], void **dev);
+int  nl_ipc_close_handle(nl_ctx *ctx, void *dev);
 int  nl_host_alloc_pinned(int64_t bytes, void **host);
 int  nl_host_free_pinned(void *host);
 int  nl_memcpy_h2d(nl_ctx *ctx, void *dev, const void *host, int64_t bytes);   /* async on the stream */

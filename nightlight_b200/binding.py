@@ -49,6 +49,7 @@ DECLARED_SYMBOLS = {
     "nl_stack_frames_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
     "nl_stack_run": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp, _i64p, _i64p]),
     "nl_stack_run_dev": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp]),
+    "nl_stack_run_dev_bcast": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(_vp), C.c_int32]),
     "nl_stack_clip_counts": (C.c_int, [_vp, _i64p, _i64p]),
     "nl_stack_end": (C.c_int, [_vp]),
     "nl_auto_select_mode": (C.c_int, [C.c_int32]),
@@ -65,6 +66,9 @@ DECLARED_SYMBOLS = {
     "nl_synth_fill_dev": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32]),
     "nl_dev_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "nl_dev_free": (C.c_int, [_vp, _vp]),
+    "nl_ipc_get_handle": (C.c_int, [_vp, _vp, C.c_char_p]),
+    "nl_ipc_open_handle": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "nl_ipc_close_handle": (C.c_int, [_vp, _vp]),
     "nl_host_alloc_pinned": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
     "nl_host_free_pinned": (C.c_int, [_vp]),
     "nl_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
@@ -168,6 +172,20 @@ class Context:
         check(load_library().nl_memcpy_d2h(self._h, host_array.ctypes.data_as(_vp), _vp(dev), host_array.nbytes))
         self.sync()
 
+    # cross-process peer mapping (CUDA IPC)
+    def ipc_handle(self, dev):
+        buf = C.create_string_buffer(64)
+        check(load_library().nl_ipc_get_handle(self._h, _vp(dev), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = _vp()
+        check(load_library().nl_ipc_open_handle(self._h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dev):
+        check(load_library().nl_ipc_close_handle(self._h, _vp(dev)))
+
     def synth_fill(self, dev, p0, count, frame, seed=12345):
         check(load_library().nl_synth_fill_dev(self._h, _vp(dev), int(p0), int(count), int(frame), int(seed)))
 
@@ -242,6 +260,15 @@ class StackJob:
         """asynchronous; result stays in device memory at dev_out"""
         w, wp = self._weights(weights, self.n_frames)
         check(load_library().nl_stack_run_dev(self._h, int(mode), wp, sigma_low, sigma_high, ref_frame_loc, _vp(dev_out)))
+        if w is not None:
+            self.ctx.sync()
+
+    def run_dev_bcast(self, mode, dev_out, peer_outs, weights=None, sigma_low=2.75, sigma_high=2.75, ref_frame_loc=0.0):
+        """like run_dev, and the result is also stored to every device pointer of peer_outs (peer stripes)"""
+        w, wp = self._weights(weights, self.n_frames)
+        arr = (_vp * max(len(peer_outs), 1))(*[_vp(p) for p in peer_outs])
+        check(load_library().nl_stack_run_dev_bcast(self._h, int(mode), wp, sigma_low, sigma_high, ref_frame_loc, _vp(dev_out),
+                                                    arr, len(peer_outs)))
         if w is not None:
             self.ctx.sync()
 

@@ -5,6 +5,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace nl {
 
@@ -129,6 +130,35 @@ int nl_dev_free(nl_ctx *ctx, void *dev) {
     CtxGuard g(ctx);
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     NL_CUDA(cudaFree(dev));
+    return NL_OK;
+}
+
+// Cross-process peer mapping (one process per GPU): the owner exports a cudaMalloc'ed buffer, every
+// other rank opens it and gets a pointer it can hand to nl_stack_run_dev_bcast as a peer stripe.
+int nl_ipc_get_handle(nl_ctx *ctx, void *dev, unsigned char handle[64]) {
+    NL_REQUIRE(ctx && dev && handle, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CtxGuard g(ctx);
+    cudaIpcMemHandle_t h;
+    NL_CUDA(cudaIpcGetMemHandle(&h, dev));
+    memcpy(handle, &h, 64);
+    return NL_OK;
+}
+
+int nl_ipc_open_handle(nl_ctx *ctx, const unsigned char handle[64], void **dev) {
+    NL_REQUIRE(ctx && dev && handle, "NULL argument");
+    CtxGuard g(ctx);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    NL_CUDA(cudaIpcOpenMemHandle(dev, h, cudaIpcMemLazyEnablePeerAccess));
+    return NL_OK;
+}
+
+int nl_ipc_close_handle(nl_ctx *ctx, void *dev) {
+    NL_REQUIRE(ctx, "ctx is NULL");
+    CtxGuard g(ctx);
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    NL_CUDA(cudaIpcCloseMemHandle(dev));
     return NL_OK;
 }
 

@@ -9,6 +9,8 @@
 
 #include "../../include/nightlight_cuda.h"
 
+#define NL_MAX_PEERS 8
+
 struct nl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;

@@ -31,11 +31,21 @@ struct StackArgs {
     const float *ramp;       // [2*(n+1)] MeanStdDev of 0..c-1, linear fit only
     float ref_loc, sig_lo, sig_hi;
     float *out;              // [pixels]
+    float *peer_out[NL_MAX_PEERS];   // further copies of the result (peer-mapped stripes of the gathered image)
+    int n_peers;
     unsigned long long *clip;   // [2] low, high
     unsigned long long *tile_counter;   // next tile of the dynamic scheduler (zeroed per launch)
 };
 
 __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+
+// Result store.  Multi-GPU: the reassembly of the stacked image is fused into this epilogue -- besides
+// the local copy, every warp stores its 128-byte result segment straight into the gathered image of
+// each peer GPU (peer-mapped memory over NVLink), so no separate all-gather pass runs afterwards.
+__device__ __forceinline__ void store_result(const StackArgs &a, long long p, float v) {
+    a.out[p] = v;
+    for (int e = 0; e < a.n_peers; e++) a.peer_out[e][p] = v;
+}
 
 // ---- StackMean / StackMeanWeighted (stack.go:307-366) ----------------------------------------
 template <bool W, int V>   // V pixels per thread (4: float4 path, 1: scalar path)
@@ -72,8 +82,13 @@ __global__ void __launch_bounds__(256) stack_mean_kernel(StackArgs a) {
 #pragma unroll
         for (int c = 0; c < V; c++)
             r[c] = num[c] == 0 ? a.ref_loc : __fdiv_rn(sum[c], W ? wsum[c] : (float)num[c]);
-        if (V == 4) *reinterpret_cast<float4 *>(a.out + p) = make_float4(r[0], r[1 % V], r[2 % V], r[3 % V]);
-        else a.out[p] = r[0];
+        if (V == 4) {
+            const float4 q = make_float4(r[0], r[1 % V], r[2 % V], r[3 % V]);
+            *reinterpret_cast<float4 *>(a.out + p) = q;
+            for (int e = 0; e < a.n_peers; e++) *reinterpret_cast<float4 *>(a.peer_out[e] + p) = q;
+        } else {
+            store_result(a, p, r[0]);
+        }
     }
 }
 
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
         } else {
             res = reduce_linfit<S>(g, cur, __reduce_max_sync(0xffffffffu, cur), a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
         }
-        if (valid) a.out[p] = cur == 0 ? a.ref_loc : res;         // stack.go:388-397
+        if (valid) store_result(a, p, cur == 0 ? a.ref_loc : res);   // stack.go:388-397
         __syncwarp();
         t = tn;
     }
@@ -272,7 +287,7 @@ static int launch_mean(nl_stack_job *job, const StackArgs &args) {
 }
 
 static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, float sig_lo, float sig_hi,
-                        float ref_loc, float *dev_out) {
+                        float ref_loc, float *dev_out, float *const *peer_outs = nullptr, int n_peers = 0) {
     nl_ctx *ctx = job->ctx;
     if (mode < NL_ST_MEDIAN || mode > NL_ST_AUTO) return set_error(NL_E_INVALID, "invalid stacking mode");   // stack.go:118-120
     if (mode == NL_ST_AUTO) mode = auto_select_mode(job->n);
@@ -293,6 +308,8 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     a.frames = job->frames; a.stride = job->pixels; a.pixels = job->pixels; a.n = job->n;
     a.weights = weighted ? job->weights : nullptr; a.ramp = job->ramp;
     a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip; a.tile_counter = job->clip + 2;
+    a.n_peers = n_peers;
+    for (int e = 0; e < NL_MAX_PEERS; e++) a.peer_out[e] = e < n_peers ? peer_outs[e] : nullptr;
     switch (mode) {
     case NL_ST_MEDIAN: return launch_column_s<ST_MEDIAN, false>(job, a);     // weights ignored, stack.go:160-161
     case NL_ST_MEAN: return weighted ? launch_mean<true>(job, a) : launch_mean<false>(job, a);
@@ -388,6 +405,23 @@ int nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, floa
     NL_REQUIRE(job && (dev_out || job->pixels == 0), "NULL argument");
     CtxGuard g(job->ctx);
     int rc = stack_launch(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, dev_out);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(job->clip_host, job->clip, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            job->ctx->stream));
+    return NL_OK;
+}
+
+int nl_stack_run_dev_bcast(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                           float ref_frame_loc, float *dev_out, float *const *peer_outs, int32_t n_peers) {
+    NL_REQUIRE(job && (dev_out || job->pixels == 0), "NULL argument");
+    NL_REQUIRE(n_peers >= 0 && n_peers <= NL_MAX_PEERS && (n_peers == 0 || peer_outs), "bad peer list");
+    const bool vec = (job->pixels % 4) == 0;
+    for (int e = 0; e < n_peers; e++) {
+        NL_REQUIRE(peer_outs[e], "NULL peer pointer");
+        NL_REQUIRE(!vec || (reinterpret_cast<uintptr_t>(peer_outs[e]) % 16) == 0, "peer stripes must be 16-byte aligned");
+    }
+    CtxGuard g(job->ctx);
+    int rc = stack_launch(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, dev_out, peer_outs, n_peers);
     if (rc != NL_OK) return rc;
     NL_CUDA(cudaMemcpyAsync(job->clip_host, job->clip, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             job->ctx->stream));

@@ -50,3 +50,37 @@ def allreduce_clip_counts(clip_low: int, clip_high: int, device, group=None):
     t = torch.tensor([clip_low, clip_high], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t[0].item()), int(t[1].item())
+
+
+class PeerGather:
+    """The gathered image, allocated on every rank and peer-mapped on every other rank (CUDA IPC over
+    NVLink / NVSwitch), so that the stack kernel's epilogue can store rank r's stripe straight into
+    everybody's image (nl_stack_run_dev_bcast) -- the all-gather is fused into the producing kernel.
+    Equal stripes of `stripe_px` pixels; rank r's stripe lives at element offset r*stripe_px."""
+
+    def __init__(self, ctx, stripe_px, group=None):
+        import torch.distributed as dist
+        self.ctx, self.stripe_px, self.group = ctx, int(stripe_px), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buf = ctx.dev_alloc(4 * self.stripe_px * self.world)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, ctx.ipc_handle(self.buf), group=group)
+        self.peers = [self.buf if r == self.rank else ctx.ipc_open(h) for r, h in enumerate(handles)]
+        off = 4 * self.rank * self.stripe_px
+        self.local_out = self.buf + off
+        self.peer_outs = [p + off for r, p in enumerate(self.peers) if r != self.rank]
+
+    def to_host(self):
+        import numpy as np
+        out = np.empty(self.stripe_px * self.world, dtype=np.float32)
+        self.ctx.d2h(out, self.buf)
+        return out
+
+    def close(self):
+        import torch.distributed as dist
+        self.ctx.sync()
+        dist.barrier(group=self.group)            # nobody may still be storing into a buffer that goes away
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.ctx.ipc_close(p)
+        self.ctx.dev_free(self.buf)

@@ -201,3 +201,27 @@ def test_goal_seek_matches_oracle_driven_search(ctx):
             want = nl.find_sigmas_and_stack(lambda sl, sh: O.stack(frames, name, sl, sh), mode, n, p, lo, hi)
             assert got[1:] == want[1:], (name, got[1:], want[1:])
             assert bits_equal(got[0], want[0]), (name, first_mismatch(got[0], want[0]))
+
+
+def test_bcast_epilogue_stores_every_copy(ctx):
+    """nl_stack_run_dev_bcast: the result also lands in every extra (peer) buffer -- the fused
+    reassembly epilogue, here with two more buffers on the same device"""
+    frames = O.synth_frames(20, 77, 4100)           # 4100 % 4 == 0 -> float4 path of the mean kernel too
+    n, p = frames.shape
+    bufs = [ctx.dev_alloc(4 * p) for _ in range(3)]
+    try:
+        with nl.StackJob(ctx, n, p) as job:
+            for i in range(n):
+                job.put_frame(i, frames[i])
+            for mode, name in ((nl.ST_SIGMA, "sigma"), (nl.ST_MEAN, "mean"), (nl.ST_LINEAR_FIT, "linfit")):
+                job.run_dev_bcast(mode, bufs[0], bufs[1:])
+                ctx.sync()
+                want = O.stack(frames, name)
+                for b in bufs:
+                    got = np.empty(p, np.float32)
+                    ctx.d2h(got, b)
+                    assert bits_equal(got, want[0]), name
+                assert job.clip_counts() == want[1:]
+    finally:
+        for b in bufs:
+            ctx.dev_free(b)
