@@ -18,6 +18,8 @@
 #include "nl_internal.h"
 #include "nl_column.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through the runtime, libcuda is not linked)
+
 #include <vector>
 
 namespace nl {
@@ -31,6 +33,7 @@ struct StackArgs {
     const float *ramp;       // [2*(n+1)] MeanStdDev of 0..c-1, linear fit only
     float ref_loc, sig_lo, sig_hi;
     float *out;              // [pixels]
+    int use_tma;             // tiles are staged by TMA tensor copies (16-byte aligned frame rows)
     float *peer_out[NL_MAX_PEERS];   // further copies of the result (peer-mapped stripes of the gathered image)
     int n_peers;
     unsigned long long *clip;   // [2] low, high
@@ -38,6 +41,31 @@ struct StackArgs {
 };
 
 __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+
+// ---- TMA staging of a tile: the frame stack is described by a 2-D tensor map [frame][pixel]; one
+// tensor copy moves a [32 frames x 32 pixels] box (32 rows of 128 bytes) straight from HBM/L2 into
+// the warp's [sample][lane] slab in shared memory, N/32 boxes per tile, all in flight at once and
+// completing on the warp's mbarrier.  Out-of-range pixels and frames arrive as NaN (the map's fill
+// mode), which is exactly "no sample" for the reducers.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mb, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+    return ok != 0;
+}
+// one [TMA_ROWS frames x 32 pixels] box of the frame stack -> shared memory (SASS: UTMALDG)
+constexpr int TMA_ROWS = 32;
+__device__ __forceinline__ void tma_box_g2s(unsigned dst, const CUtensorMap *tmap, int pixel0, int frame0, unsigned mb) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(pixel0), "r"(frame0), "r"(mb) : "memory");
+}
 
 // Result store.  Multi-GPU: the reassembly of the stacked image is fused into this epilogue -- besides
 // the local copy, every warp stores its 128-byte result segment straight into the gathered image of
@@ -100,8 +128,8 @@ template <int MODE, bool W, typename IDX> struct SlotBytes {
 };
 
 template <int MODE, bool W, int S, typename IDX>
-__global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n = a.n;
@@ -119,6 +147,17 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
 
     const long long tiles = (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
+
+    // one mbarrier per warp for the TMA staging, behind the last warp region
+    const unsigned mb = smem_u32(reinterpret_cast<char *>(smem) + (size_t)2 * (QW - 1) * S * 4 +
+                                 (size_t)(blockDim.x >> 5) * SB * S * npad) + 8u * warp;
+    const bool tma_tiles = S == 32 && a.use_tma;
+    unsigned tma_phase = 0;
+    if (tma_tiles) {
+        if (lane == 0) mbar_init(mb, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // make the init visible to the async proxy
+        __syncwarp();
+    }
 
     // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles from a
     // counter -- one tile ahead, so that the next tile's 128-byte row segments (one per frame) can be
@@ -139,8 +178,28 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a) {
         const long long p = t * S + lane;
         const bool valid = lane < S && p < a.pixels;
         int cur = 0;
-        if (valid) {
-            // gather the non-NaN samples of pixel p in frame order (stack.go:380-387): 32 loads
+        if (tma_tiles) {
+            // (the slab was last touched by this warp's generic-proxy loads and stores: order them
+            // before the async-proxy writes of the tensor copies)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(mb, (unsigned)npad * (S * 4));
+            __syncwarp();
+            const unsigned slab = smem_u32(region);
+            for (int j = lane; j * TMA_ROWS < npad; j += 32)
+                tma_box_g2s(slab + (unsigned)j * (TMA_ROWS * S * 4), &tmap, (int)(t * S), j * TMA_ROWS, mb);
+            while (!mbar_try_wait(mb, tma_phase)) {}
+            tma_phase ^= 1;
+            // drop the NaNs in frame order, in place (stack.go:380-387); nothing moves until the first NaN
+#pragma unroll 8
+            for (int k = 0; k < n; k++) {
+                const float v = g[k * S];
+                if (cur != k) g[cur * S] = v;
+                if (W) gw[cur * S] = (IDX)k;
+                cur += (v == v) ? 1 : 0;
+            }
+        } else if (valid) {
+            // unaligned frame rows or narrow tiles: gather the non-NaN samples through registers, 32 loads
             // in flight per lane, each a 128-byte row segment per warp
             const float *src = a.frames + p;
             int k = 0;
@@ -221,9 +280,37 @@ struct nl_stack_job {
     bool ramp_ready = false;
     unsigned long long *clip = nullptr;   // [3] device: clip low, clip high, tile counter
     unsigned long long *clip_host = nullptr;   // [2] pinned
+    alignas(64) CUtensorMap tmap;     // [n][pixels] fp32, box 32 frames x 32 pixels, NaN fill
+    bool tmap_ok = false;
 };
 
 namespace nl {
+
+// The frame stack as a 2-D tensor [frame][pixel] for the TMA staging.  cuTensorMapEncodeTiled is a
+// driver entry point; it is looked up through the runtime so that the library links cudart only.
+static bool make_frame_tensor_map(nl_stack_job *job) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)job->pixels, (cuuint64_t)job->n};
+    const cuuint64_t strides[1] = {(cuuint64_t)job->pixels * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)TMA_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(&job->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, job->frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+}
 
 template <int MODE, bool W, int S, typename IDX>
 static int launch_column(nl_stack_job *job, const StackArgs &args) {
@@ -231,11 +318,11 @@ static int launch_column(nl_stack_job *job, const StackArgs &args) {
     constexpr int SB = SlotBytes<MODE, W, IDX>::value;
     const size_t per_warp = (size_t)SB * S * ((job->n + 31) & ~31);
     const size_t pad = (size_t)2 * (QW - 1) * S * sizeof(float);
-    const size_t cap = (size_t)ctx->max_smem_optin;
+    const size_t cap = (size_t)ctx->max_smem_optin - 64;          // 64 bytes behind the slabs: the tile mbarriers
     if (per_warp + pad > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
     int warps = (int)((cap - pad) / per_warp);
     if (warps > 8) warps = 8;
-    const size_t smem = per_warp * warps + pad;
+    const size_t smem = per_warp * warps + pad + 64;
     auto kern = stack_column_kernel<MODE, W, S, IDX>;
     NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
@@ -246,7 +333,7 @@ static int launch_column(nl_stack_job *job, const StackArgs &args) {
     const long long need = (tiles + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(args);
+    kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(args, job->tmap);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;
@@ -257,7 +344,7 @@ static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     constexpr int SB = SlotBytes<MODE, W, IDX>::value;
     const size_t per_pixel = (size_t)SB * ((job->n + 31) & ~31);
     const size_t pad = (size_t)2 * (QW - 1) * sizeof(float);
-    const size_t cap = (size_t)job->ctx->max_smem_optin;
+    const size_t cap = (size_t)job->ctx->max_smem_optin - 64;
     if ((per_pixel + pad) * 32 <= cap) return launch_column<MODE, W, 32, IDX>(job, args);
     if ((per_pixel + pad) * 8 <= cap) return launch_column<MODE, W, 8, IDX>(job, args);
     return launch_column<MODE, W, 1, IDX>(job, args);
@@ -304,7 +391,9 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
         ctx->launches++;
         job->ramp_ready = true;
     }
+    if (!job->tmap_ok && (job->pixels % 4) == 0 && job->pixels < (1ll << 31)) job->tmap_ok = make_frame_tensor_map(job);
     StackArgs a;
+    a.use_tma = job->tmap_ok ? 1 : 0;
     a.frames = job->frames; a.stride = job->pixels; a.pixels = job->pixels; a.n = job->n;
     a.weights = weighted ? job->weights : nullptr; a.ramp = job->ramp;
     a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip; a.tile_counter = job->clip + 2;
