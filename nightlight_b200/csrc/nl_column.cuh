@@ -312,7 +312,10 @@ NL_HD float weighted_mean(const float *g, const IDX *gw, const float *wtab, int 
 // is clamp(g[i], L, H) with the cumulative bounds (L, H) -- recomputed on the fly here, which saves
 // the second shared-memory buffer (and its traffic) the copy would need.  `changed` counts, like the
 // reference, the samples the CURRENT round moved.
-NL_HD float clampcmp(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// clamp as two min/max instructions.  Against the reference's `if w<lo {w=lo} else if w>hi {w=hi}` this
+// can only differ in the sign of a zero (fmax(-0,+0)), which neither the strict comparisons that count
+// `changed` nor the sums of squares below can see.
+NL_HD float clampmm(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 template <int S>
 NL_HD float winsor_sigma(const float *g, int cur, float median, float sd) {
@@ -323,21 +326,21 @@ NL_HD float winsor_sigma(const float *g, int cur, float median, float sd) {
         int changed = 0;
         // clamp and first sum of MeanStdDev fused: the sum runs over the clamped values in order
         float s = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < cur; i++) {
-            float v = clampcmp(g[i * S], L, H);          // the copy as the previous rounds left it
-            if (v < lo) { v = lo; changed++; }
-            else if (v > hi) { v = hi; changed++; }
+            const float old = clampmm(g[i * S], L, H);   // the copy as the previous rounds left it
+            const float v = clampmm(old, lo, hi);
+            changed += (v != old) ? 1 : 0;               // old < lo or old > hi
             s = nl_addf(s, v);
         }
-        L = clampcmp(L, lo, hi);
-        H = clampcmp(H, lo, hi);
+        L = clampmm(L, lo, hi);
+        H = clampmm(H, lo, hi);
         const float fn = (float)cur;
         const float m = nl_divf(s, fn);
         float var = 0.0f;
 #pragma unroll 8
         for (int i = 0; i < cur; i++) {
-            const float d = nl_subf(clampcmp(g[i * S], L, H), m);
+            const float d = nl_subf(clampmm(g[i * S], L, H), m);
             var = nl_addf(var, nl_mulf(d, d));
         }
         var = nl_divf(var, fn);
