@@ -360,9 +360,54 @@ NL_HD float winsor_sigma(const float *g, int cur, float median, float sd) {
 // stored: an exchange whose upper slot is >= n is skipped.  The network is data independent, so the
 // 32 lanes (32 columns of different length n <= nmax) run it in lock step without divergence.
 // nmax: the longest column of the warp (host: n).
+// one stage of the network: compare-exchange partners `lo` (bit s clear) and lo|s, or the mirrored
+// partner lo ^ (k-1) in the first stage of a merge; K, SS compile-time -> the index arithmetic folds
+template <int S, int K, int SS, int P>
+NL_HD void sort_stage(float *a, int n) {
+    constexpr bool mirror = SS == (K >> 1);
+#pragma unroll 8
+    for (int i = 0; i < (P >> 1); i++) {
+        const int lo = ((i & ~(SS - 1)) << 1) | (i & (SS - 1));
+        const int hi = mirror ? (lo ^ (K - 1)) : (lo | SS);
+        if (hi < n) {
+            const float x = a[lo * S], y = a[hi * S];
+            a[lo * S] = fminf(x, y);
+            a[hi * S] = fmaxf(x, y);
+        }
+    }
+}
+template <int S, int K, int SS, int P>
+struct SortStages {
+    static NL_HD void run(float *a, int n) {
+        sort_stage<S, K, SS, P>(a, n);
+        SortStages<S, K, (SS >> 1), P>::run(a, n);
+    }
+};
+template <int S, int K, int P>
+struct SortStages<S, K, 0, P> {
+    static NL_HD void run(float *, int) {}
+};
+template <int S, int K, int P>
+struct SortMerges {
+    static NL_HD void run(float *a, int n) {
+        SortMerges<S, (K >> 1), P>::run(a, n);
+        SortStages<S, K, (K >> 1), P>::run(a, n);
+    }
+};
+template <int S, int P>
+struct SortMerges<S, 1, P> {
+    static NL_HD void run(float *, int) {}
+};
+
 template <int S>
 NL_HD void sort_column(float *a, int n, int nmax) {
-    int P = 1;
+    // (no NaNs and min/max instead of a swap: an exchange of equal values or of -0/+0 cannot be seen
+    // in the sorted sequence of values)
+    if (nmax <= 32) { SortMerges<S, 32, 32>::run(a, n); return; }
+    if (nmax <= 64) { SortMerges<S, 64, 64>::run(a, n); return; }
+    if (nmax <= 128) { SortMerges<S, 128, 128>::run(a, n); return; }
+    if (nmax <= 256) { SortMerges<S, 256, 256>::run(a, n); return; }
+    int P = 512;
     while (P < nmax) P <<= 1;
     for (int k = 2; k <= P; k <<= 1) {
         for (int s = k >> 1; s >= 1; s >>= 1) {
@@ -373,8 +418,8 @@ NL_HD void sort_column(float *a, int n, int nmax) {
                 const int hi = mirror ? (lo ^ (k - 1)) : (lo | s);
                 if (hi < n) {
                     const float x = a[lo * S], y = a[hi * S];
-                    a[lo * S] = y < x ? y : x;
-                    a[hi * S] = y < x ? x : y;
+                    a[lo * S] = fminf(x, y);
+                    a[hi * S] = fmaxf(x, y);
                 }
             }
         }
