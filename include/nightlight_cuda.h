@@ -97,6 +97,14 @@ int  nl_auto_select_mode(int32_t n_frames);
 int  nl_get_weights(int32_t weighting, const float *exposure, const float *noise, const float *hfr,
                     int32_t n_frames, float *weights);
 
+/* ---- noise estimate: replaces stats.EstimateNoise, portable definition (internal/stats/noise.go:24-55),
+ * the per-frame scalar behind StWeightInverseNoise (stack.go:247-259).  n_frames frames of width x height
+ * pixels, frame i at dev_frames + i*frame_stride (e.g. the buffer of a stack job holding whole frames);
+ * one launch for all frames, results to host memory. */
+int  nl_estimate_noise_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t width,
+                           int32_t height, float *host_noise);
+int  nl_estimate_noise(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float *noise);
+
 /* ---- batches: replaces StackIncremental / StackIncrementalFinalize (stack.go:924-944) -------
  * acc = light*weight (first != 0) or acc += light*weight; then acc *= 1/weight_sum.  Device buffers. */
 int  nl_stack_incremental_dev(nl_ctx *ctx, float *dev_acc, const float *dev_light, int64_t pixels, float weight, int first);

@@ -54,6 +54,8 @@ DECLARED_SYMBOLS = {
     "nl_stack_end": (C.c_int, [_vp]),
     "nl_auto_select_mode": (C.c_int, [C.c_int32]),
     "nl_get_weights": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, _fp]),
+    "nl_estimate_noise_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _fp]),
+    "nl_estimate_noise": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _fp]),
     "nl_stack_incremental_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_int]),
     "nl_stack_incremental_finalize_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_float]),
     "nl_transform_invert": (C.c_int, [_fp, _fp]),
@@ -271,6 +273,14 @@ class StackJob:
                                                     arr, len(peer_outs)))
         if w is not None:
             self.ctx.sync()
+
+    def frame_noise(self, width):
+        """stats.EstimateNoise of every resident frame (whole frames of `width` columns) -> float32[n_frames]"""
+        base, stride = self.frames_dev
+        out = np.empty(self.n_frames, dtype=np.float32)
+        check(load_library().nl_estimate_noise_dev(self.ctx.handle, _vp(base), self.n_frames, stride, int(width),
+                                                   self.pixels // int(width), out.ctypes.data_as(_fp)))
+        return out
 
     def clip_counts(self):
         cl, ch = C.c_int64(), C.c_int64()

@@ -64,11 +64,17 @@ class OpStack:
         """OpStack.Apply, stack.go:115-227"""
         if self.mode < B.ST_MEDIAN or self.mode > B.ST_AUTO:
             raise NightlightError(B.NL_E_INVALID, "invalid stacking mode")
-        weights = get_weights(frames, self.weighting)
         pixels = int(np.asarray(frames[0].data).size)
         with B.StackJob(ctx, len(frames), pixels) as job:
             for i, f in enumerate(frames):
                 job.put_frame(i, f.data)
+            if self.weighting == B.W_INVERSE_NOISE and any(f.noise is None for f in frames) and len(frames[0].naxisn) >= 1:
+                # the reference's Stats.Noise() is computed lazily from the frame (stats.go, noise.go:24-55);
+                # here for all resident frames in one launch
+                for f, nz in zip(frames, job.frame_noise(int(frames[0].naxisn[0]))):
+                    if f.noise is None:
+                        f.noise = float(nz)
+            weights = get_weights(frames, self.weighting)
             data, cl, ch = job.run(self.mode, weights, self.sigmaLow, self.sigmaHigh, self.refFrameLoc)
         exposure = np.float32(0)
         for f in frames:                  # stack.go:220-221, sequential fp32 sum
@@ -115,6 +121,14 @@ class OpStackBatches:
             ctx.dev_free(acc)
             ctx.dev_free(tmp)
         return Image(data=out, naxisn=tuple(batches[0][0].naxisn), exposure=float(exposure))
+
+
+def estimate_noise(ctx: B.Context, data, width):
+    """stats.EstimateNoise (portable definition, noise.go:24-55) of one frame -> float32"""
+    data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+    out = C.c_float()
+    check(load_library().nl_estimate_noise(ctx.handle, data.ctypes.data_as(C.c_void_p), data.size, int(width), C.byref(out)))
+    return np.float32(out.value)
 
 
 def transform_invert(trans):

@@ -125,3 +125,36 @@ def test_config3_pipeline_detect_project_stack(ctx):
         want = O.stack(fc, mode)
         assert bits_equal(got[0], want[0]), (mode, first_mismatch(got[0], want[0]))
         assert got[1:] == want[1:]
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (333, 257), (3, 3), (5, 4), (1024, 1024)])
+def test_estimate_noise_matches_oracle(ctx, w, h):
+    """stats.EstimateNoise (portable definition) on the device: bit-exact against the oracle"""
+    import ctypes as C
+    rng = np.random.default_rng(w + h)
+    img = (rng.standard_normal(w * h) * 11 + 500).astype(np.float32)
+    O.lib().nlo_estimate_noise.restype = C.c_float
+    want = np.float32(O.lib().nlo_estimate_noise(img.ctypes.data_as(C.POINTER(C.c_float)), w, h))
+    got = nl.estimate_noise(ctx, img, w)
+    assert got.view(np.uint32) == want.view(np.uint32) or (np.isnan(got) and np.isnan(want)), (got, want)
+
+
+def test_inverse_noise_weights_from_resident_frames(ctx):
+    """BASELINE configs[1] mode: winsorized sigma-clip + noise-weighted mean; the per-frame noise is
+    estimated on the device for all resident frames in one launch"""
+    import ctypes as C
+    from nightlight_b200.ops import Image, OpStack
+    w, h, n = 96, 64, 18
+    rng = np.random.default_rng(2)
+    frames = [(rng.standard_normal(w * h) * (5 + k % 4) + 300).astype(np.float32) for k in range(n)]
+    O.lib().nlo_estimate_noise.restype = C.c_float
+    noise = np.array([O.lib().nlo_estimate_noise(f.ctypes.data_as(C.POINTER(C.c_float)), w, h) for f in frames], np.float32)
+    with nl.StackJob(ctx, n, w * h) as job:
+        for i, f in enumerate(frames):
+            job.put_frame(i, f)
+        got = job.frame_noise(w)
+    assert np.array_equal(got.view(np.uint32), noise.view(np.uint32))
+    weights = (np.float32(1) / (np.float32(1) + np.float32(4) * (noise - noise.min()) / (noise.max() - noise.min()))).astype(np.float32)
+    res = OpStack(mode=nl.ST_WINSOR_SIGMA, weighting=nl.W_INVERSE_NOISE).apply([Image(data=f, naxisn=(w, h)) for f in frames], ctx)
+    want = O.stack(np.stack(frames), "winsor", weights=weights)
+    assert bits_equal(res.data, want[0]) and (res.clip_low, res.clip_high) == want[1:]
