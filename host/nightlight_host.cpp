@@ -259,6 +259,12 @@ std::vector<Star> FindStars(Context &c, const std::vector<float> &data, int32_t 
     return stars;
 }
 
+float EstimateNoise(Context &c, const std::vector<float> &data, int32_t width) {
+    float noise = 0;
+    check(nl_estimate_noise(c.Device(0), data.data(), (int32_t)data.size(), width, &noise));
+    return noise;
+}
+
 float EstimateNoise(const std::vector<float> &data, int32_t width) {
     static const float w[9] = {1, -2, 1, -2, 4, -2, 1, -2, 1};
     const int32_t off[9] = {-width - 1, -width, -width + 1, -1, 0, 1, width - 1, width, width + 1};

@@ -64,7 +64,7 @@ int main(int argc, char **argv) {
             op.SigmaLow = (float)atof(flag["stSigLow"].c_str());
             op.SigmaHigh = (float)atof(flag["stSigHigh"].c_str());
             if (op.Weighting == StWeightInverseNoise)
-                for (auto &im : imgs) im->Noise = EstimateNoise(im->Data, im->Naxisn[0]);
+                for (auto &im : imgs) im->Noise = EstimateNoise(c, im->Data, im->Naxisn[0]);
             std::vector<const Image *> f;
             for (auto &im : imgs) f.push_back(im.get());
             Image res;
@@ -84,7 +84,7 @@ int main(int argc, char **argv) {
             for (auto &im : imgs) {
                 float loc = (float)atof(flag["loc"].c_str()), scale = (float)atof(flag["scale"].c_str());
                 if (std::isnan(loc)) loc = im->Mean;            // the reference's estimators are randomised: inputs here
-                if (std::isnan(scale)) scale = EstimateNoise(im->Data, im->Naxisn[0]);
+                if (std::isnan(scale)) scale = EstimateNoise(c, im->Data, im->Naxisn[0]);
                 float sos = 0, hfr = 0;
                 im->Stars = FindStars(c, im->Data, im->Naxisn[0], loc, scale, (float)atof(flag["starSig"].c_str()),
                                       (float)atof(flag["starBpSig"].c_str()), (float)atof(flag["starInOut"].c_str()),
