@@ -345,9 +345,28 @@ static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     const size_t per_pixel = (size_t)SB * ((job->n + 31) & ~31);
     const size_t pad = (size_t)2 * (QW - 1) * sizeof(float);
     const size_t cap = (size_t)job->ctx->max_smem_optin - 64;
-    if ((per_pixel + pad) * 32 <= cap) return launch_column<MODE, W, 32, IDX>(job, args);
-    if ((per_pixel + pad) * 8 <= cap) return launch_column<MODE, W, 8, IDX>(job, args);
-    return launch_column<MODE, W, 1, IDX>(job, args);
+    // Tile width: a wide tile uses every lane of a warp but needs SB*npad*S bytes per warp, and the kernel
+    // lives on latency hiding across warps (each column is a serial dependency chain).  Score = columns
+    // that make progress per cycle ~ min(warps, 12) * S; e.g. N=256 -> 32 pixels x 7 warps, N=1024 ->
+    // 8 pixels x 7 warps instead of 32 pixels x 1 warp.
+    const int widths[4] = {32, 16, 8, 1};
+    int best = 0;
+    double best_score = -1;
+    for (int wdt : widths) {
+        const size_t per_warp = (per_pixel + pad) * wdt;
+        if (per_warp > cap) continue;
+        size_t warps = cap / per_warp;
+        if (warps > 64) warps = 64;
+        const double score = (double)(warps > 12 ? 12 : warps) * wdt;
+        if (score > best_score) { best_score = score; best = wdt; }
+    }
+    switch (best) {
+    case 32: return launch_column<MODE, W, 32, IDX>(job, args);
+    case 16: return launch_column<MODE, W, 16, IDX>(job, args);
+    case 8: return launch_column<MODE, W, 8, IDX>(job, args);
+    case 1: return launch_column<MODE, W, 1, IDX>(job, args);
+    }
+    return set_error(NL_E_INVALID, "n_frames %d too large for shared memory", job->n);
 }
 
 template <int MODE, bool W>

@@ -97,6 +97,14 @@ def test_many_frames_small_tile_path(ctx):
         check_against_oracle(ctx, frames, mode, weighted)
 
 
+def test_512_and_1024_frames_medium_tile_paths(ctx):
+    """512 frames -> 16-pixel tiles, 1024 frames (BASELINE config 4's depth) -> 8-pixel tiles"""
+    for n, pixels in ((512, 200), (1024, 90)):
+        frames = O.synth_frames(n, 7 * n, pixels)
+        for mode, weighted in (("sigma", False), ("linfit", False), ("winsor", True), ("median", False)):
+            check_against_oracle(ctx, frames, mode, weighted)
+
+
 def test_empty_and_errors(ctx):
     with nl.StackJob(ctx, 3, 0) as job:
         res, cl, ch = job.run(nl.ST_SIGMA)

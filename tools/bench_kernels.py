@@ -89,6 +89,19 @@ def main():
         job.close()
         del out
 
+    # ---- BASELINE config 4 depth: 1024 frames, linear fit (a row-stripe sample of the 8192-wide image) ----
+    if "linfit1024" in only or (not only and not args.quick):
+        n, pixels = 1024, 8192 * 8
+        job = nl.StackJob(ctx, n, pixels)
+        job.synth_fill()
+        out = torch.empty(pixels, dtype=torch.float32, device=dev)
+        for name, mode in (("linfit", nl.ST_LINEAR_FIT), ("sigma", nl.ST_SIGMA)):
+            ms = timed(lambda: job.run_dev(mode, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=3)
+            report("stack<%s> n=1024" % name, "%d x 8192x8 fp32 (inputs %.2f GiB > L2)" % (n, 4.0 * n * pixels / 2**30),
+                   4.0 * (n + 1) * pixels, ms, {"mpx_in_per_s": n * pixels / ms / 1e3})
+        job.close()
+        del out
+
     # ---- resample: 6000x4000 -> 6000x4000, rotation 0.5 deg + shift ---------------------------------
     if not only or "project" in only:
         w, h = (3000, 2000) if args.quick else (6000, 4000)
