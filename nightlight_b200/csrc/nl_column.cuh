@@ -31,8 +31,12 @@
 // lanes of the warp (lanes without a pixel pass n = 0).
 #if defined(__CUDA_ARCH__)
 #define NL_ANY(x) (__any_sync(0xffffffffu, (x)))
+#define NL_WARP_MIN(x) (__reduce_min_sync(0xffffffffu, (x)))
+#define NL_WARP_MAX(x) (__reduce_max_sync(0xffffffffu, (x)))
 #else
 #define NL_ANY(x) (x)
+#define NL_WARP_MIN(x) (x)
+#define NL_WARP_MAX(x) (x)
 #endif
 
 namespace nl {
@@ -111,7 +115,11 @@ struct ColMem {
     }
     static __device__ __forceinline__ void st(pos_t p, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(p), "f"(v)); }
     static __device__ __forceinline__ pos_t add(pos_t p, int elems) { return p + (unsigned)(elems * (S * 4)); }
-    static __device__ __forceinline__ int diff(pos_t a, pos_t b) { return (int)(a - b) / (S * 4); }
+    // raw position arithmetic: one element = UNIT raw units (bytes here), so that the bookkeeping of the
+    // quick-select needs no scaling of pointer differences
+    static constexpr int UNIT = S * 4;
+    static __device__ __forceinline__ pos_t add_raw(pos_t p, int raw) { return p + (unsigned)raw; }
+    static __device__ __forceinline__ int diff_raw(pos_t a, pos_t b) { return (int)(a - b); }
 #else
     typedef float *pos_t;
     static pos_t at(const float *a) { return const_cast<float *>(a); }
@@ -119,7 +127,9 @@ struct ColMem {
     static float ld(pos_t p) { return p[J * S]; }
     static void st(pos_t p, float v) { *p = v; }
     static pos_t add(pos_t p, int elems) { return p + elems * S; }
-    static int diff(pos_t a, pos_t b) { return (int)((a - b) / S); }
+    static constexpr int UNIT = S;                         // raw units = floats on the host
+    static pos_t add_raw(pos_t p, int raw) { return p + raw; }
+    static int diff_raw(pos_t a, pos_t b) { return (int)(a - b); }
 #endif
 };
 
@@ -172,10 +182,12 @@ template <int S, bool GATE = false>
 NL_HD float qselect(float *a, int n, int k) {
     typedef ColMem<S> M;
     typedef typename M::pos_t P;
+    constexpr int U = M::UNIT;                               // raw position units per element (power of two)
     P left = M::at(a), right = M::add(left, n > 0 ? n - 1 : 0);
     bool active = n > 1;
     P l = left, r = right;
     float pivot = M::template ld<0>(M::add(left, (n > 0 ? n - 1 : 0) >> 1));
+    int kraw = k * U;                                        // k, the partition sizes and the scan distances in raw units
     bool any_active = NL_ANY(active);
     while (any_active) {
 #pragma unroll
@@ -185,31 +197,32 @@ NL_HD float qselect(float *a, int n, int k) {
             load_window<M, QW, -1>(r, rw);
             const bool sl = lw[0] >= pivot;                  // left scan stops here  (qsort.go:104-108)
             const bool sr = rw[0] <= pivot;                  // right scan stops here (qsort.go:109-113)
-            int tl = QW, tr = QW;                            // first stop among the window slots 1..QW-1
+            int tl = QW * U, tr = QW * U;                    // first stop among the window slots 1..QW-1
 #pragma unroll
             for (int j = QW - 1; j >= 1; j--) {
-                tl = (lw[j] >= pivot) ? j : tl;
-                tr = (rw[j] <= pivot) ? j : tr;
+                tl = (lw[j] >= pivot) ? j * U : tl;
+                tr = (rw[j] <= pivot) ? j * U : tr;
             }
-            const int d = M::diff(r, l);
+            const int d = M::diff_raw(r, l);
             const bool sw = sl & sr & (d > 0);               // both stopped, not crossed: swap (qsort.go:114-115)
             if (sw) { M::st(l, rw[0]); M::st(r, lw[0]); }
-            const bool near = d < QW;                        // the windows saw slots the swap has just changed
-            const int step = (sw & near) ? 1 : 0;
-            int dl = (!sl | sw) ? (step ? 1 : tl) : 0;
-            int dr = (!sr | sw) ? (step ? 1 : tr) : 0;
+            const bool near = d < QW * U;                    // the windows saw slots the swap has just changed
+            const bool step = sw & near;
+            int dl = (!sl | sw) ? (step ? U : tl) : 0;
+            int dr = (!sr | sw) ? (step ? U : tr) : 0;
             if (GATE) { dl = active ? dl : 0; dr = active ? dr : 0; }
-            l = M::add(l, dl);
-            r = M::add(r, -dr);
+            l = M::add_raw(l, dl);
+            r = M::add_raw(r, -dr);
         }
         const bool cross = active & (M::template ld<0>(l) >= pivot) & (M::template ld<0>(r) <= pivot) & !(l < r);
         if (NL_ANY(cross)) {                                 // qsort.go:114: partition index = r
             if (cross) {
-                const int offset = M::diff(r, left) + 1;
-                if (k <= offset) right = r;
-                else { left = M::add(r, 1); k -= offset; }
+                const int offset = M::diff_raw(r, left) + U;
+                if (kraw <= offset) right = r;
+                else { left = M::add_raw(r, U); kraw -= offset; }
                 active = left < right;
-                pivot = M::template ld<0>(M::add(left, M::diff(right, left) >> 1));
+                // a[(left+right)>>1]: half the distance, rounded down to a whole element
+                pivot = M::template ld<0>(M::add_raw(left, (M::diff_raw(right, left) >> 1) & ~(U - 1)));
                 l = left;
                 r = active ? right : left;
             }
@@ -259,15 +272,32 @@ NL_HD void mean_stddev(const float *a, int n, float &mean, float &sd) {
 // free), and only the set bits are then resolved one by one in ascending order exactly like the
 // reference does (replace by the last sample, re-test the slot, stop at the shrinking end).
 // Reads up to 31 slots past `cur`: buffers are padded to a multiple of 32 slots.
-template <int S, bool W, typename IDX>
-NL_HD int clip_pass(float *g, IDX *gw, int cur, float lo, float hi, int &ncl, int &nch) {
-    for (int b = 0; NL_ANY(b < cur); b += 32) {
-        unsigned bad = 0;
+// One-sided scan: right after the quick-select the buffer is partitioned around slot km1 = n>>1 (the
+// upper median): slots below hold values <= median, slots from km1 on values >= median.  With
+// non-negative sigmas (lo <= median <= hi) a slot below km1 can only violate the lower bound and a slot
+// from km1 on only the upper bound, so whole 32-slot blocks on either side need one comparison per
+// sample instead of two (`onesided` is warp-uniform; blocks that straddle some lane's km1 test both).
+template <int SIDE, int S>
+NL_HD unsigned clip_mask32(const float *g, int b, float lo, float hi) {
+    unsigned bad = 0;
 #pragma unroll
-        for (int u = 0; u < 32; u++) {
-            const float v = g[(b + u) * S];
-            bad |= ((v < lo) | (v > hi)) ? (1u << u) : 0u;
-        }
+    for (int u = 0; u < 32; u++) {
+        const float v = g[(b + u) * S];
+        const bool o = SIDE < 0 ? (v < lo) : (SIDE > 0 ? (v > hi) : ((v < lo) | (v > hi)));
+        bad |= o ? (1u << u) : 0u;
+    }
+    return bad;
+}
+
+template <int S, bool W, typename IDX>
+NL_HD int clip_pass(float *g, IDX *gw, int cur, float lo, float hi, int &ncl, int &nch, int km1 = 0, bool onesided = false) {
+    const int kmin = onesided ? NL_WARP_MIN(cur > 0 ? km1 : 0x7fffffff) : 0;
+    const int kmax = onesided ? NL_WARP_MAX(cur > 0 ? km1 : 0) : 0x7fffffff;
+    for (int b = 0; NL_ANY(b < cur); b += 32) {
+        unsigned bad;
+        if (b + 32 <= kmin) bad = clip_mask32<-1, S>(g, b, lo, hi);
+        else if (b >= kmax) bad = clip_mask32<1, S>(g, b, lo, hi);
+        else bad = clip_mask32<0, S>(g, b, lo, hi);
         const int rem = cur - b;
         bad &= rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
         while (NL_ANY(bad != 0)) {
@@ -464,7 +494,7 @@ NL_HD float reduce_sigma(float *g, IDX *gw, const float *wtab, int cur, float si
         mean_stddev<S>(g, m, mean, sd);
         const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
         const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-        const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch);
+        const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch, m >> 1, sig_lo >= 0.0f && sig_hi >= 0.0f);
         if (!done) {
             if (left == cur || left <= 1) {
                 result = W ? weighted_mean<S, IDX>(g, gw, wtab, left) : mean;
@@ -489,7 +519,7 @@ NL_HD float reduce_winsor(float *g, IDX *gw, const float *wtab, int cur, float s
         if (m > 0) sd = winsor_sigma<S>(g, m, median, sd);
         const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
         const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-        const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch);
+        const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch, m >> 1, sig_lo >= 0.0f && sig_hi >= 0.0f);
         if (!done) {
             if (left == cur || left <= 1) {
                 result = W ? weighted_mean<S, IDX>(g, gw, wtab, left) : mean;
@@ -511,7 +541,7 @@ NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi,
     float sd = nl_mulf(mad, 1.4826f);
     float lo = nl_subf(median, nl_mulf(sig_lo, sd));
     float hi = nl_addf(median, nl_mulf(sig_hi, sd));
-    cur = clip_pass<S, false, unsigned char>(g, nullptr, cur, lo, hi, ncl, nch);
+    cur = clip_pass<S, false, unsigned char>(g, nullptr, cur, lo, hi, ncl, nch, cur >> 1, sig_lo >= 0.0f && sig_hi >= 0.0f);
     float s = 0.0f;
     for (int i = 0; i < cur; i++) s = nl_addf(s, g[i * S]);
     return nl_divf(s, (float)cur);

@@ -20,6 +20,7 @@
 
 #include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through the runtime, libcuda is not linked)
 
+#include <stdlib.h>
 #include <vector>
 
 namespace nl {
@@ -347,7 +348,7 @@ static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     const size_t cap = (size_t)job->ctx->max_smem_optin - 64;
     // Tile width: a wide tile uses every lane of a warp but needs SB*npad*S bytes per warp, and the kernel
     // lives on latency hiding across warps (each column is a serial dependency chain).  Score = columns
-    // that make progress per cycle ~ min(warps, 12) * S; e.g. N=256 -> 32 pixels x 7 warps, N=1024 ->
+    // that make progress per cycle ~ min(warps, 8) * S; e.g. N=256 -> 32 pixels x 7 warps, N=1024 ->
     // 8 pixels x 7 warps instead of 32 pixels x 1 warp.
     const int widths[4] = {32, 16, 8, 1};
     int best = 0;
@@ -357,8 +358,12 @@ static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
         if (per_warp > cap) continue;
         size_t warps = cap / per_warp;
         if (warps > 64) warps = 64;
-        const double score = (double)(warps > 12 ? 12 : warps) * wdt;
+        const double score = (double)(warps > 8 ? 8 : warps) * wdt;
         if (score > best_score) { best_score = score; best = wdt; }
+    }
+    if (const char *force = getenv("NL_TILE_WIDTH")) {             // development override (A/B measurements)
+        const int wdt = atoi(force);
+        if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + pad) * wdt <= cap) best = wdt;
     }
     switch (best) {
     case 32: return launch_column<MODE, W, 32, IDX>(job, args);

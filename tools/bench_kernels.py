@@ -90,6 +90,15 @@ def main():
         del out
 
     # ---- BASELINE config 4 depth: 1024 frames, linear fit (a row-stripe sample of the 8192-wide image) ----
+    for n512 in ((512,) if "n512" in only else ()):
+        n, pixels = 512, 4096 * 32
+        job = nl.StackJob(ctx, n, pixels)
+        job.synth_fill()
+        out = torch.empty(pixels, dtype=torch.float32, device=dev)
+        ms = timed(lambda: job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=3)
+        report("stack<sigma> n=512 tile=%s" % os.environ.get("NL_TILE_WIDTH", "auto"), "%d x 4096x32" % n, 4.0 * (n + 1) * pixels, ms)
+        job.close()
+        del out
     if "linfit1024" in only or (not only and not args.quick):
         n, pixels = 1024, 8192 * 8
         job = nl.StackJob(ctx, n, pixels)
@@ -97,7 +106,7 @@ def main():
         out = torch.empty(pixels, dtype=torch.float32, device=dev)
         for name, mode in (("linfit", nl.ST_LINEAR_FIT), ("sigma", nl.ST_SIGMA)):
             ms = timed(lambda: job.run_dev(mode, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=3)
-            report("stack<%s> n=1024" % name, "%d x 8192x8 fp32 (inputs %.2f GiB > L2)" % (n, 4.0 * n * pixels / 2**30),
+            report("stack<%s> n=1024 tile=%s" % (name, os.environ.get("NL_TILE_WIDTH", "auto")), "%d x 8192x8 fp32 (inputs %.2f GiB > L2)" % (n, 4.0 * n * pixels / 2**30),
                    4.0 * (n + 1) * pixels, ms, {"mpx_in_per_s": n * pixels / ms / 1e3})
         job.close()
         del out
