@@ -174,7 +174,7 @@ template <typename M, int N, int DIR>
 NL_HD void load_window(typename M::pos_t p, float *w) { WindowLoader<M, N, DIR>::run(p, w); }
 
 #ifndef NL_QSTEPS
-#define NL_QSTEPS 4
+#define NL_QSTEPS 6
 #endif
 constexpr int QSTEPS = NL_QSTEPS;   // steps between two checks for crossed scans
 
