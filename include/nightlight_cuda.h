@@ -144,6 +144,8 @@ int  nl_ipc_open_handle(nl_ctx *ctx, const unsigned char handle[64], void **dev)
 int  nl_ipc_close_handle(nl_ctx *ctx, void *dev);
 int  nl_host_alloc_pinned(int64_t bytes, void **host);
 int  nl_host_free_pinned(void *host);
+int  nl_host_register(void *host, int64_t bytes);     /* page-lock an existing buffer in place (cudaHostRegister) */
+int  nl_host_unregister(void *host);
 int  nl_memcpy_h2d(nl_ctx *ctx, void *dev, const void *host, int64_t bytes);   /* async on the stream */
 int  nl_memcpy_d2h(nl_ctx *ctx, void *host, const void *dev, int64_t bytes);   /* async on the stream */
 

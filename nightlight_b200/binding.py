@@ -73,6 +73,8 @@ DECLARED_SYMBOLS = {
     "nl_ipc_close_handle": (C.c_int, [_vp, _vp]),
     "nl_host_alloc_pinned": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
     "nl_host_free_pinned": (C.c_int, [_vp]),
+    "nl_host_register": (C.c_int, [_vp, C.c_int64]),
+    "nl_host_unregister": (C.c_int, [_vp]),
     "nl_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "nl_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
 }

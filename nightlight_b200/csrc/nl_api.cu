@@ -170,6 +170,19 @@ int nl_host_alloc_pinned(int64_t bytes, void **host) {
     return NL_OK;
 }
 
+// Page-lock an existing host buffer in place (e.g. a Go []float32 that stays alive and is not moved:
+// Go's heap is non-moving) so that nl_stack_put_frame / nl_project copy from it at full PCIe speed.
+int nl_host_register(void *host, int64_t bytes) {
+    NL_REQUIRE(host && bytes > 0, "bad argument");
+    NL_CUDA(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterPortable));
+    return NL_OK;
+}
+
+int nl_host_unregister(void *host) {
+    NL_CUDA(cudaHostUnregister(host));
+    return NL_OK;
+}
+
 int nl_host_free_pinned(void *host) {
     NL_CUDA(cudaFreeHost(host));
     return NL_OK;

@@ -563,12 +563,21 @@ NL_HD float reduce_linfit(float *g, int cur, int nmax, const float *ramp, float 
         const int m = done ? 0 : cur;
         // LinearRegression(xs, ys), stats.go:569-586
         const float xm = ramp[2 * m], xsd = ramp[2 * m + 1];
-        float ym, ysd;
-        mean_stddev<S>(g, m, ym, ysd);
-        float corr = 0.0f;
-#pragma unroll 4
-        for (int i = 0; i < m; i++)
-            corr = nl_addf(corr, nl_mulf(nl_subf((float)i, xm), nl_subf(g[i * S], ym)));
+        // MeanStdDev(ys) (stats.go:246-261) with the covariance sum of LinearRegression (stats.go:575-579)
+        // riding on its second pass: three independent sequential chains, each in the reference's order
+        float ysum = 0.0f;
+#pragma unroll 8
+        for (int i = 0; i < m; i++) ysum = nl_addf(ysum, g[i * S]);
+        const float fm = (float)m;
+        const float ym = nl_divf(ysum, fm);
+        float yvar = 0.0f, corr = 0.0f;
+#pragma unroll 8
+        for (int i = 0; i < m; i++) {
+            const float d = nl_subf(g[i * S], ym);
+            yvar = nl_addf(yvar, nl_mulf(d, d));
+            corr = nl_addf(corr, nl_mulf(nl_subf((float)i, xm), d));
+        }
+        const float ysd = nl_sqrtf(nl_divf(yvar, fm));
         corr = nl_divf(corr, nl_mulf(nl_mulf(xsd, ysd), nl_addf((float)m, 1.0f)));
         const float slope = nl_divf(nl_mulf(corr, ysd), xsd);
         const float icpt = nl_subf(ym, nl_mulf(slope, xm));
