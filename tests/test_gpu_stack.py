@@ -233,3 +233,20 @@ def test_bcast_epilogue_stores_every_copy(ctx):
     finally:
         for b in bufs:
             ctx.dev_free(b)
+
+
+def test_infinities_denormals_and_huge_values(ctx):
+    """IEEE corner values go through the same comparisons and fp32 sums as in the reference: +-inf
+    samples, denormals (no flush-to-zero), magnitudes whose squares overflow"""
+    rng = np.random.default_rng(21)
+    n, p = 40, 600
+    frames = (rng.standard_normal((n, p)) * 10 + 100).astype(np.float32)
+    frames[3, 0:50] = np.inf
+    frames[7, 25:80] = -np.inf
+    frames[:, 100:150] = (rng.standard_normal((n, 50)) * 1e-41).astype(np.float32)      # denormals
+    frames[:, 150:200] = (rng.standard_normal((n, 50)) * 1e30).astype(np.float32)       # squares overflow to inf
+    frames[5, 200:220] = np.float32(3e38)
+    frames[:, 220:240] = -0.0
+    frames[::2, 230:240] = 0.0
+    for mode, weighted in mode_cases():
+        check_against_oracle(ctx, frames, mode, weighted)
