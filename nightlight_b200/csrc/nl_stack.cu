@@ -160,22 +160,13 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         __syncwarp();
     }
 
-    // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles from a
-    // counter -- one tile ahead, so that the next tile's 128-byte row segments (one per frame) can be
-    // prefetched into L2 while this tile is being reduced (~100 us later the gather finds them there)
+    // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles from a counter
     auto next_tile = [&]() {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(a.tile_counter, 1ull);
         return (long long)__shfl_sync(0xffffffffu, v, 0);
     };
-    long long t = next_tile();
-    while (t < tiles) {
-        const long long tn = next_tile();
-        if (tn < tiles) {
-            const float *nsrc = a.frames + tn * S;
-            for (int k = lane; k < n; k += 32)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (long long)k * a.stride));
-        }
+    for (long long t = next_tile(); t < tiles; t = next_tile()) {
         const long long p = t * S + lane;
         const bool valid = lane < S && p < a.pixels;
         int cur = 0;
@@ -240,7 +231,6 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         }
         if (valid) store_result(a, p, cur == 0 ? a.ref_loc : res);   // stack.go:388-397
         __syncwarp();
-        t = tn;
     }
     if (MODE >= ST_SIGMA) {
         // clip totals (stack.go:193-198): warp reduce, one atomic pair per warp
