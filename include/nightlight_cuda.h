@@ -119,6 +119,25 @@ int  nl_project(nl_ctx *ctx, const float *host_src, int32_t src_w, int32_t src_h
 int  nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t src_w, int32_t src_h,
                     float *dev_dst, int32_t dst_w, int32_t dst_h, const float trans[6], float out_of_bounds);
 
+/* Resample fused with the histogram match that runs just before it (OpMatchHistogram -> Image.MatchHistogram,
+ * internal/ops/post/postprocess.go:74-94, internal/fits/pixelops.go:601-612): every source sample is read as
+ * d*multiplier + offset (mul, then add), which saves one full pass over the frame. */
+int  nl_project_scaled(nl_ctx *ctx, const float *host_src, int32_t src_w, int32_t src_h, float *host_dst, int32_t dst_w,
+                       int32_t dst_h, const float trans[6], float out_of_bounds, float multiplier, float offset);
+int  nl_project_scaled_dev(nl_ctx *ctx, const float *dev_src, int32_t src_w, int32_t src_h, float *dev_dst, int32_t dst_w,
+                           int32_t dst_h, const float trans[6], float out_of_bounds, float multiplier, float offset);
+
+/* ---- FITS pixel payload: replaces the conversion loops of internal/fits/read.go:176-443 (big-endian BITPIX
+ * 8/16/32/64/-32/-64 -> fp32, v = float32(val)*Bscale + Bzero) and write.go:182-215 (fp32 -> big-endian,
+ * NaN -> 0).  nl_stack_put_frame_raw uploads a frame as its raw payload (half the PCIe bytes for 16-bit
+ * frames) and decodes it into the job on the device. */
+int  nl_fits_decode(nl_ctx *ctx, const void *host_raw, int32_t bitpix, int64_t count, float bscale, float bzero, float *host_dst);
+int  nl_fits_decode_dev(nl_ctx *ctx, const void *dev_raw, int32_t bitpix, int64_t count, float bscale, float bzero, float *dev_dst);
+int  nl_fits_encode(nl_ctx *ctx, const float *host_src, int64_t count, void *host_raw);
+int  nl_fits_encode_dev(nl_ctx *ctx, const float *dev_src, int64_t count, void *dev_raw);
+int  nl_stack_put_frame_raw(nl_stack_job *job, int32_t i, const void *host_raw, int32_t bitpix, int64_t count, float bscale,
+                            float bzero);
+
 /* ---- star detection: replaces star.FindStars (internal/star/findstars.go:59-100) -----------
  * nl_find_bright = findBrightPixels (findstars.go:105-129): candidates in raster order.  *count is
  * the true number found; at most cap are stored. */

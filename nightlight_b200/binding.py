@@ -61,6 +61,13 @@ DECLARED_SYMBOLS = {
     "nl_transform_invert": (C.c_int, [_fp, _fp]),
     "nl_project": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float]),
     "nl_project_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float]),
+    "nl_project_scaled": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float, C.c_float]),
+    "nl_project_scaled_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float, C.c_float]),
+    "nl_fits_decode": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float, _vp]),
+    "nl_fits_decode_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float, _vp]),
+    "nl_fits_encode": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "nl_fits_encode_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "nl_stack_put_frame_raw": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float]),
     "nl_find_bright": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, C.c_int32, _i32p]),
     "nl_find_bright_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, C.c_int32, _i32p]),
     "nl_find_stars": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -229,6 +236,13 @@ class StackJob:
         # stay valid until the next sync
         a = _f32(host).reshape(-1)
         check(load_library().nl_stack_put_frame(self._h, int(i), a.ctypes.data_as(_vp), a.size))
+
+    def put_frame_raw(self, i, raw, bitpix, bscale=1.0, bzero=0.0):
+        """raw: the frame's big-endian FITS payload (bytes / uint8 array); decoded on the device"""
+        a = np.frombuffer(raw, dtype=np.uint8) if isinstance(raw, (bytes, bytearray, memoryview)) else np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+        count = a.size // (abs(int(bitpix)) // 8)
+        check(load_library().nl_stack_put_frame_raw(self._h, int(i), a.ctypes.data_as(_vp), int(bitpix), count, bscale, bzero))
+        self.ctx.sync()                     # `a` may be a temporary
 
     @property
     def frames_dev(self):

@@ -28,6 +28,7 @@ namespace nl {
 int set_error(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int ensure_scratch(nl_ctx *ctx, size_t bytes);
+int fits_decode_launch(nl_ctx *ctx, const void *dev_raw, int bitpix, long long n, float bscale, float bzero, float *dev_dst);
 
 #define NL_CUDA(call)                                        \
     do {                                                     \

@@ -11,8 +11,11 @@ namespace nl {
 struct Affine { float a, b, c, d, e, f; };
 
 // One destination pixel, exactly the reference's expression shapes.
+// SCALE: every gathered source sample first becomes d*mult + offset (mul, then add), i.e. the result is
+// that of Image.MatchHistogram (internal/fits/pixelops.go:601-612) followed by Project, in one pass.
+template <bool SCALE>
 __device__ __forceinline__ float project_pixel(const float *__restrict__ src, int sw, int sh, const Affine &inv, int col,
-                                               int row, float oob) {
+                                               int row, float oob, float mult, float offset) {
     const float x = (float)col, y = (float)row;
     // coord.go:141-145: (A*x + B*y) + C
     const float px = __fadd_rn(__fadd_rn(__fmul_rn(inv.a, x), __fmul_rn(inv.b, y)), inv.c);
@@ -24,7 +27,11 @@ __device__ __forceinline__ float project_pixel(const float *__restrict__ src, in
         const int xl = (int)fx, yl = (int)fy;
         const float xr = __fsub_rn(px, fx), yr = __fsub_rn(py, fy);
         const float *s = src + (size_t)yl * sw + xl;
-        const float d00 = __ldg(s), d10 = __ldg(s + 1), d01 = __ldg(s + sw), d11 = __ldg(s + sw + 1);
+        float d00 = __ldg(s), d10 = __ldg(s + 1), d01 = __ldg(s + sw), d11 = __ldg(s + sw + 1);
+        if (SCALE) {
+            d00 = __fadd_rn(__fmul_rn(d00, mult), offset); d10 = __fadd_rn(__fmul_rn(d10, mult), offset);
+            d01 = __fadd_rn(__fmul_rn(d01, mult), offset); d11 = __fadd_rn(__fmul_rn(d11, mult), offset);
+        }
         const float ox = __fsub_rn(1.0f, xr), oy = __fsub_rn(1.0f, yr);
         const float vyl = __fadd_rn(__fmul_rn(d00, ox), __fmul_rn(d10, xr));   // project.go:68-70
         const float vyh = __fadd_rn(__fmul_rn(d01, ox), __fmul_rn(d11, xr));
@@ -37,14 +44,15 @@ __device__ __forceinline__ float project_pixel(const float *__restrict__ src, in
 // destination pixels of a row, so every one of the 16 gathers of a thread is a (nearly) contiguous
 // 128-byte warp access and every store a full 128-byte line; the four rows give each thread 16
 // independent loads in flight and their 2x2 footprints share L1 lines with the rows above and below.
-__global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ src, int sw, int sh,
-                                                      float *__restrict__ dst, int dw, int dh, Affine inv, float oob) {
+template <bool SCALE>
+__global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ src, int sw, int sh, float *__restrict__ dst,
+                                                      int dw, int dh, Affine inv, float oob, float mult, float offset) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
     if (col >= dw || row0 >= dh) return;
     float v[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel(src, sw, sh, inv, col, row0 + r, oob) : 0.0f;
+    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, col, row0 + r, oob, mult, offset) : 0.0f;
 #pragma unroll
     for (int r = 0; r < 4; r++)
         if (row0 + r < dh) __stcs(dst + (size_t)(row0 + r) * dw + col, v[r]);
@@ -75,8 +83,8 @@ int nl_transform_invert(const float t[6], float inv[6]) {
     return NL_OK;
 }
 
-int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, float *dev_dst, int32_t dw, int32_t dh,
-                   const float trans[6], float oob) {
+static int project_launch(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, float *dev_dst, int32_t dw, int32_t dh,
+                          const float trans[6], float oob, bool scale, float mult, float offset) {
     NL_REQUIRE(ctx && trans, "NULL argument");
     NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0, "negative image size");
     float inv[6];
@@ -88,14 +96,25 @@ int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, fl
     Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
     dim3 block(64, 4);
     dim3 grid((dw + block.x - 1) / block.x, (dh + 4 * block.y - 1) / (4 * block.y));
-    project_kernel<<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob);
+    if (scale) project_kernel<true><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob, mult, offset);
+    else project_kernel<false><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob, 1.0f, 0.0f);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;
 }
 
-int nl_project(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t sh, float *host_dst, int32_t dw, int32_t dh,
-               const float trans[6], float oob) {
+int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, float *dev_dst, int32_t dw, int32_t dh,
+                   const float trans[6], float oob) {
+    return project_launch(ctx, dev_src, sw, sh, dev_dst, dw, dh, trans, oob, false, 1.0f, 0.0f);
+}
+
+int nl_project_scaled_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, float *dev_dst, int32_t dw, int32_t dh,
+                          const float trans[6], float oob, float multiplier, float offset) {
+    return project_launch(ctx, dev_src, sw, sh, dev_dst, dw, dh, trans, oob, true, multiplier, offset);
+}
+
+static int project_host(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t sh, float *host_dst, int32_t dw, int32_t dh,
+                        const float trans[6], float oob, bool scale, float mult, float offset) {
     NL_REQUIRE(ctx && trans, "NULL argument");
     NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0, "negative image size");
     float inv[6];
@@ -110,11 +129,21 @@ int nl_project(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t sh, float
     if (rc != NL_OK) return rc;
     float *ds = (float *)ctx->scratch, *dd = (float *)((char *)ctx->scratch + soff);
     if (sbytes) NL_CUDA(cudaMemcpyAsync(ds, host_src, sbytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = nl_project_dev(ctx, ds, sw, sh, dd, dw, dh, trans, oob);
+    rc = project_launch(ctx, ds, sw, sh, dd, dw, dh, trans, oob, scale, mult, offset);
     if (rc != NL_OK) return rc;
     NL_CUDA(cudaMemcpyAsync(host_dst, dd, dbytes, cudaMemcpyDeviceToHost, ctx->stream));
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     return NL_OK;
+}
+
+int nl_project(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t sh, float *host_dst, int32_t dw, int32_t dh,
+               const float trans[6], float oob) {
+    return project_host(ctx, host_src, sw, sh, host_dst, dw, dh, trans, oob, false, 1.0f, 0.0f);
+}
+
+int nl_project_scaled(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t sh, float *host_dst, int32_t dw, int32_t dh,
+                      const float trans[6], float oob, float multiplier, float offset) {
+    return project_host(ctx, host_src, sw, sh, host_dst, dw, dh, trans, oob, true, multiplier, offset);
 }
 
 }  // extern "C"

@@ -496,6 +496,28 @@ int nl_stack_put_frame(nl_stack_job *job, int32_t i, const float *host, int64_t 
     return NL_OK;
 }
 
+// A frame handed over as its raw FITS payload (big-endian BITPIX samples): uploaded as is -- half the
+// PCIe bytes for 16-bit camera frames -- and decoded into the job's frame slot on the device
+// (read.go:176-443: v = float32(val)*Bscale + Bzero).
+int nl_stack_put_frame_raw(nl_stack_job *job, int32_t i, const void *host_raw, int32_t bitpix, int64_t count, float bscale,
+                           float bzero) {
+    NL_REQUIRE(job && host_raw, "NULL argument");
+    NL_REQUIRE(i >= 0 && i < job->n, "frame index out of range");
+    NL_REQUIRE(count == job->pixels, "frame size differs from the job's pixel count");
+    NL_REQUIRE(bitpix == 8 || bitpix == 16 || bitpix == 32 || bitpix == 64 || bitpix == -32 || bitpix == -64, "Unknown BITPIX value");
+    if (count == 0) return NL_OK;
+    nl_ctx *ctx = job->ctx;
+    CtxGuard g(ctx);
+    const size_t bytes = (size_t)count * (size_t)(bitpix < 0 ? -bitpix : bitpix) / 8;
+    // two staging halves used alternately: the upload of frame i+1 may start while frame i is decoded
+    const size_t half = (bytes + 255) & ~(size_t)255;
+    int rc = ensure_scratch(ctx, 2 * half);
+    if (rc != NL_OK) return rc;
+    void *stage = (char *)ctx->scratch + (size_t)(i & 1) * half;
+    NL_CUDA(cudaMemcpyAsync(stage, host_raw, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return fits_decode_launch(ctx, stage, bitpix, count, bscale, bzero, job->frames + (size_t)i * job->pixels);
+}
+
 int nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_stride) {
     NL_REQUIRE(job && dev_frames, "NULL argument");
     *dev_frames = job->frames;

@@ -153,6 +153,37 @@ def project(ctx: B.Context, src, src_w, src_h, dst_w, dst_h, trans, out_of_bound
     return dst
 
 
+def project_scaled(ctx: B.Context, src, src_w, src_h, dst_w, dst_h, trans, multiplier, offset, out_of_bounds=float("nan")):
+    """Image.MatchHistogram (pixelops.go:601-612: d*multiplier + offset) fused into (*Image).Project"""
+    src = np.ascontiguousarray(src, dtype=np.float32).reshape(-1)
+    if src.size != src_w * src_h:
+        raise NightlightError(B.NL_E_INVALID, "source size does not match its dimensions")
+    dst = np.empty(dst_w * dst_h, dtype=np.float32)
+    t = np.ascontiguousarray(trans, dtype=np.float32)
+    check(load_library().nl_project_scaled(ctx.handle, src.ctypes.data_as(C.c_void_p), src_w, src_h,
+                                           dst.ctypes.data_as(C.c_void_p), dst_w, dst_h,
+                                           t.ctypes.data_as(C.POINTER(C.c_float)), out_of_bounds, multiplier, offset))
+    return dst
+
+
+def fits_decode(ctx: B.Context, raw, bitpix, bscale=1.0, bzero=0.0):
+    """the reader's conversion loop (read.go:176-443): big-endian payload -> float32(val)*Bscale + Bzero"""
+    a = np.frombuffer(raw, dtype=np.uint8) if isinstance(raw, (bytes, bytearray, memoryview)) else np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    count = a.size // (abs(int(bitpix)) // 8)
+    out = np.empty(count, dtype=np.float32)
+    check(load_library().nl_fits_decode(ctx.handle, a.ctypes.data_as(C.c_void_p), int(bitpix), count, bscale, bzero,
+                                        out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def fits_encode(ctx: B.Context, data):
+    """the writer's conversion loop (write.go:182-215): float32 -> big-endian bytes, NaN -> 0"""
+    a = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+    out = np.empty(4 * a.size, dtype=np.uint8)
+    check(load_library().nl_fits_encode(ctx.handle, a.ctypes.data_as(C.c_void_p), a.size, out.ctypes.data_as(C.c_void_p)))
+    return out.tobytes()
+
+
 def find_bright_pixels(ctx: B.Context, data, width, threshold, radius):
     """findBrightPixels, findstars.go:105-129 -> structured array of star.Star in raster order"""
     data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)

@@ -158,3 +158,59 @@ def test_inverse_noise_weights_from_resident_frames(ctx):
     res = OpStack(mode=nl.ST_WINSOR_SIGMA, weighting=nl.W_INVERSE_NOISE).apply([Image(data=f, naxisn=(w, h)) for f in frames], ctx)
     want = O.stack(np.stack(frames), "winsor", weights=weights)
     assert bits_equal(res.data, want[0]) and (res.clip_low, res.clip_high) == want[1:]
+
+
+def test_project_scaled_equals_match_histogram_then_project(ctx):
+    """N1: the histogram match d*mult + offset (pixelops.go:601-612) fused into the resample"""
+    rng = np.random.default_rng(31)
+    w, h = 300, 200
+    src = (rng.standard_normal(w * h) * 40 + 700).astype(np.float32)
+    mult, off = np.float32(1.0371), np.float32(-12.625)
+    matched = (src * mult).astype(np.float32) + off            # mul, then add, both rounded to fp32
+    th = np.deg2rad(0.7)
+    trans = np.array([np.cos(th), -np.sin(th), 3.25, np.sin(th), np.cos(th), -4.5], np.float32)
+    got = nl.project_scaled(ctx, src, w, h, w, h, trans, mult, off)
+    want = O.project(matched.astype(np.float32), w, h, w, h, trans, np.float32(np.nan))
+    assert bits_equal(got, want), first_mismatch(got, want)
+
+
+@pytest.mark.parametrize("bitpix", [8, 16, 32, 64, -32, -64])
+def test_fits_payload_decode_encode(ctx, bitpix):
+    """N1: the reader's / writer's conversion loops on the device (read.go:176-443, write.go:182-215)"""
+    rng = np.random.default_rng(40 + bitpix)
+    n = 10007
+    dt = {8: ">u1", 16: ">i2", 32: ">i4", 64: ">i8", -32: ">f4", -64: ">f8"}[bitpix]
+    if bitpix == 8:
+        disk = rng.integers(0, 256, n).astype(dt)
+    elif bitpix > 0:
+        lim = 2 ** (bitpix - 1) - 1
+        disk = rng.integers(-lim, lim, n).astype(dt)
+    else:
+        disk = (rng.standard_normal(n) * 1e3).astype(dt)
+    bscale, bzero = (np.float32(1), np.float32(32768)) if bitpix == 16 else (np.float32(1.5), np.float32(-0.25))
+    got = nl.fits_decode(ctx, disk.tobytes(), bitpix, float(bscale), float(bzero))
+    val = disk.astype(dt[1:]).astype(np.float32)
+    want = (val * bscale).astype(np.float32) + bzero
+    assert bits_equal(got, want.astype(np.float32)), first_mismatch(got, want)
+    # encode: NaN -> 0, network byte order
+    data = want.astype(np.float32).copy()
+    data[::97] = np.nan
+    raw = nl.fits_encode(ctx, data)
+    back = np.frombuffer(raw, dtype=">f4").astype(np.float32)
+    expect = data.copy()
+    expect[np.isnan(expect)] = 0
+    assert np.array_equal(back.view(np.uint32), expect.view(np.uint32))
+
+
+def test_stack_from_raw_int16_payloads(ctx):
+    """frames uploaded as raw 16-bit FITS payloads (half the PCIe bytes), decoded on the device, stacked"""
+    rng = np.random.default_rng(50)
+    n, p = 12, 5000
+    adu = rng.integers(-32768, 32767, (n, p)).astype(">i2")
+    frames = (adu.astype(np.int16).astype(np.float32) * np.float32(1)).astype(np.float32) + np.float32(32768)
+    with nl.StackJob(ctx, n, p) as job:
+        for i in range(n):
+            job.put_frame_raw(i, adu[i].tobytes(), 16, 1.0, 32768.0)
+        got = job.run(nl.ST_SIGMA)
+    want = O.stack(frames, "sigma")
+    assert bits_equal(got[0], want[0]) and got[1:] == want[1:]

@@ -125,6 +125,25 @@ def main():
                {"mpx_per_s": w * h / ms / 1e3})
         del src, dst
 
+    # ---- N1: resample fused with the histogram match, FITS payload decode (16-bit) and encode ---------
+    if not only or "fits" in only:
+        w, h = (3000, 2000) if args.quick else (6000, 4000)
+        src = torch.empty(w * h, dtype=torch.float32, device=dev)
+        dst = torch.empty(w * h, dtype=torch.float32, device=dev)
+        ctx.synth_fill(src.data_ptr(), 0, w * h, 0)
+        th = np.deg2rad(0.5)
+        trans = (C.c_float * 6)(np.cos(th), -np.sin(th), 7.25, np.sin(th), np.cos(th), -3.5)
+        ms = timed(lambda: nl.binding.check(lib.nl_project_scaled_dev(ctx.handle, C.c_void_p(src.data_ptr()), w, h, C.c_void_p(dst.data_ptr()),
+                                                                      w, h, trans, float("nan"), 1.03, -5.0)))
+        report("project_kernel<scaled> (match histogram fused)", "%dx%d, L2 flushed" % (w, h), 8.0 * w * h, ms)
+        raw = torch.randint(-32768, 32767, (w * h,), dtype=torch.int16, device=dev)
+        ms = timed(lambda: nl.binding.check(lib.nl_fits_decode_dev(ctx.handle, C.c_void_p(raw.data_ptr()), 16, w * h, 1.0, 32768.0,
+                                                                   C.c_void_p(dst.data_ptr()))))
+        report("fits_decode_kernel<16>", "%d samples, L2 flushed" % (w * h), 6.0 * w * h, ms)
+        ms = timed(lambda: nl.binding.check(lib.nl_fits_encode_dev(ctx.handle, C.c_void_p(src.data_ptr()), w * h, C.c_void_p(dst.data_ptr()))))
+        report("fits_encode_kernel", "%d samples, L2 flushed" % (w * h), 8.0 * w * h, ms)
+        del src, dst, raw
+
     # ---- star candidate scan: 6000x4000 sky noise + 0.02 % bright pixels --------------------------------
     if not only or "bright" in only:
         w, h = (3000, 2000) if args.quick else (6000, 4000)
