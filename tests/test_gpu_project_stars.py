@@ -177,7 +177,7 @@ def test_project_scaled_equals_match_histogram_then_project(ctx):
 @pytest.mark.parametrize("bitpix", [8, 16, 32, 64, -32, -64])
 def test_fits_payload_decode_encode(ctx, bitpix):
     """N1: the reader's / writer's conversion loops on the device (read.go:176-443, write.go:182-215)"""
-    rng = np.random.default_rng(40 + bitpix)
+    rng = np.random.default_rng(140 + bitpix)
     n = 10007
     dt = {8: ">u1", 16: ">i2", 32: ">i4", 64: ">i8", -32: ">f4", -64: ">f8"}[bitpix]
     if bitpix == 8:
