@@ -86,6 +86,7 @@ int nl_ctx_destroy(nl_ctx *ctx) {
     CtxGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->list) cudaFree(ctx->list);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return NL_OK;

@@ -21,6 +21,8 @@ struct nl_ctx {
     // scratch owned by the context, grown on demand (star scan)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *list = nullptr;            // candidate list of the star scan (kept apart from `scratch`, which holds the row offsets)
+    size_t list_bytes = 0;
 };
 
 namespace nl {

@@ -148,18 +148,21 @@ static int bright_write(nl_ctx *ctx, const float *dev_data, int len, int width, 
     int *row_count = (int *)ctx->scratch, *row_offset = row_count + rows;
     const int threads = 256, warps_per_cta = threads / 32;
     const unsigned grid = (unsigned)((rows + warps_per_cta - 1) / warps_per_cta);
-    // the list lives in its own allocation so the offsets in the context scratch stay valid
-    nl_star *dev_list = nullptr;
-    NL_CUDA(cudaMalloc(&dev_list, sizeof(nl_star) * (size_t)keep));
+    // the list lives in its own (reused, grown on demand) allocation so the offsets in the context scratch stay valid
+    const size_t need = sizeof(nl_star) * (size_t)keep;
+    if (ctx->list_bytes < need) {
+        if (ctx->list) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFree(ctx->list)); ctx->list = nullptr; ctx->list_bytes = 0; }
+        const size_t grow = need + need / 2 + 4096;
+        NL_CUDA(cudaMalloc(&ctx->list, grow));
+        ctx->list_bytes = grow;
+    }
+    nl_star *dev_list = (nl_star *)ctx->list;
     bright_rows_kernel<true><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
                                                                row_offset, dev_list, keep);
-    cudaError_t e = cudaGetLastError();
+    NL_CUDA(cudaGetLastError());
     ctx->launches++;
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(host_out, dev_list, sizeof(nl_star) * (size_t)keep, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dev_list);
-    if (e != cudaSuccess) return cuda_fail(e, "bright pixel scan");
+    NL_CUDA(cudaMemcpyAsync(host_out, dev_list, need, cudaMemcpyDeviceToHost, ctx->stream));
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));
     return NL_OK;
 }
 
