@@ -138,9 +138,12 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
     constexpr int SB = SlotBytes<MODE, W, IDX>::value;
     // column element i of this lane's pixel at g[i*S]; lanes beyond a narrow tile alias a valid
     // column but never get samples (cur = 0) and never store
-    // (QW-1 rows of padding in front of the first and behind the last warp region: the quick-select
-    // windows may read, never use, up to QW-1 slots outside a column)
-    char *region = reinterpret_cast<char *>(smem) + (size_t)(QW - 1) * S * 4 + (size_t)warp * SB * S * npad;
+    // (a gap of QW-1 rows in front of, between and behind the warp slabs: the quick-select windows may
+    // read, never use, up to QW-1 slots outside a column -- they land in a gap nobody writes, never in
+    // another warp's live data)
+    constexpr size_t GAP = (size_t)(QW - 1) * S * 4;
+    const size_t slab_bytes = (size_t)SB * S * npad;
+    char *region = reinterpret_cast<char *>(smem) + GAP + (size_t)warp * (slab_bytes + GAP);
     float *g = reinterpret_cast<float *>(region) + (lane % S);
     float *sc = g + (size_t)S * npad;                             // MAD scratch column
     IDX *gw = reinterpret_cast<IDX *>(region + (size_t)4 * (MODE == ST_MAD ? 2 : 1) * S * npad) + (lane % S);
@@ -149,9 +152,10 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
     const long long tiles = (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
 
-    // one mbarrier per warp for the TMA staging, behind the last warp region
-    const unsigned mb = smem_u32(reinterpret_cast<char *>(smem) + (size_t)2 * (QW - 1) * S * 4 +
-                                 (size_t)(blockDim.x >> 5) * SB * S * npad) + 8u * warp;
+    // one mbarrier per warp for the TMA staging, in the last 64 bytes of the last gap (32-pixel tiles only:
+    // at N = 256 the seven slabs and eight gaps fill the 232 448 bytes a CTA may use to the byte; a window
+    // load of the last warp that strays there reads the barrier words as meaningless sample data)
+    const unsigned mb = smem_u32(reinterpret_cast<char *>(smem) + GAP + (size_t)(blockDim.x >> 5) * (slab_bytes + GAP) - 64) + 8u * warp;
     const bool tma_tiles = S == 32 && a.use_tma;
     unsigned tma_phase = 0;
     if (tma_tiles) {
@@ -307,13 +311,13 @@ template <int MODE, bool W, int S, typename IDX>
 static int launch_column(nl_stack_job *job, const StackArgs &args) {
     nl_ctx *ctx = job->ctx;
     constexpr int SB = SlotBytes<MODE, W, IDX>::value;
-    const size_t per_warp = (size_t)SB * S * ((job->n + 31) & ~31);
-    const size_t pad = (size_t)2 * (QW - 1) * S * sizeof(float);
-    const size_t cap = (size_t)ctx->max_smem_optin - 64;          // 64 bytes behind the slabs: the tile mbarriers
-    if (per_warp + pad > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
-    int warps = (int)((cap - pad) / per_warp);
+    const size_t gap = (size_t)(QW - 1) * S * sizeof(float);      // in front of, between and behind the warp slabs
+    const size_t per_warp = (size_t)SB * S * ((job->n + 31) & ~31) + gap;
+    const size_t cap = (size_t)ctx->max_smem_optin;
+    if (per_warp + gap > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
+    int warps = (int)((cap - gap) / per_warp);
     if (warps > 8) warps = 8;
-    const size_t smem = per_warp * warps + pad + 64;
+    const size_t smem = per_warp * warps + gap;                   // (the tile mbarriers live in the tail of the last gap)
     auto kern = stack_column_kernel<MODE, W, S, IDX>;
     NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
@@ -334,8 +338,8 @@ template <int MODE, bool W, typename IDX>
 static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     constexpr int SB = SlotBytes<MODE, W, IDX>::value;
     const size_t per_pixel = (size_t)SB * ((job->n + 31) & ~31);
-    const size_t pad = (size_t)2 * (QW - 1) * sizeof(float);
-    const size_t cap = (size_t)job->ctx->max_smem_optin - 64;
+    const size_t gap = (size_t)(QW - 1) * sizeof(float);           // per pixel of tile width
+    const size_t cap = (size_t)job->ctx->max_smem_optin;
     // Tile width: a wide tile uses every lane of a warp but needs SB*npad*S bytes per warp, and the kernel
     // lives on latency hiding across warps (each column is a serial dependency chain).  Score = columns
     // that make progress per cycle ~ min(warps, 8) * S; e.g. N=256 -> 32 pixels x 7 warps, N=1024 ->
@@ -344,16 +348,16 @@ static int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     int best = 0;
     double best_score = -1;
     for (int wdt : widths) {
-        const size_t per_warp = (per_pixel + pad) * wdt;
-        if (per_warp > cap) continue;
-        size_t warps = cap / per_warp;
+        const size_t per_warp = (per_pixel + gap) * wdt;
+        if (per_warp + gap * wdt > cap) continue;
+        size_t warps = (cap - gap * wdt) / per_warp;
         if (warps > 64) warps = 64;
         const double score = (double)(warps > 8 ? 8 : warps) * wdt;
         if (score > best_score) { best_score = score; best = wdt; }
     }
     if (const char *force = getenv("NL_TILE_WIDTH")) {             // development override (A/B measurements)
         const int wdt = atoi(force);
-        if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + pad) * wdt <= cap) best = wdt;
+        if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + 2 * gap) * wdt <= cap) best = wdt;
     }
     switch (best) {
     case 32: return launch_column<MODE, W, 32, IDX>(job, args);
