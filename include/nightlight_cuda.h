@@ -63,6 +63,9 @@ int  nl_ctx_destroy(nl_ctx *ctx);
 int  nl_ctx_sync(nl_ctx *ctx);                    /* wait for the context's stream */
 int  nl_ctx_stream(nl_ctx *ctx, void **stream);   /* the cudaStream_t, for event timing by the caller */
 int  nl_ctx_device(nl_ctx *ctx, int *device);
+/* free / total device memory: the budget OpStackBatches.partition (stackbatches.go:121-210) sizes its batches
+ * from takes the place of the reference's StackMemoryMB (a share of host RAM) */
+int  nl_ctx_mem_info(nl_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 int  nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches);
 

@@ -14,6 +14,6 @@ from .binding import (  # noqa: F401
     W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR, DECLARED_SYMBOLS,
 )
 from .ops import (OpStack, OpStackBatches, project, transform_invert, find_bright_pixels, find_stars, get_weights,  # noqa: F401
-                  find_sigmas_and_stack, estimate_noise, project_scaled, fits_decode, fits_encode)
+                  find_sigmas_and_stack, estimate_noise, project_scaled, fits_decode, fits_encode, partition)
 
 __version__ = "0.1.0"

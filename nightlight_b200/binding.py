@@ -43,6 +43,7 @@ DECLARED_SYMBOLS = {
     "nl_ctx_sync": (C.c_int, [_vp]),
     "nl_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "nl_ctx_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "nl_ctx_mem_info": (C.c_int, [_vp, _i64p, _i64p]),
     "nl_ctx_launch_count": (C.c_int, [_vp, _i64p]),
     "nl_stack_begin": (C.c_int, [_vp, C.c_int32, C.c_int64, C.POINTER(_vp)]),
     "nl_stack_put_frame": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
@@ -157,6 +158,12 @@ class Context:
         s = _vp()
         check(load_library().nl_ctx_stream(self._h, C.byref(s)))
         return s.value or 0
+
+    def mem_info(self):
+        """(free, total) bytes of device memory"""
+        f, t = C.c_int64(), C.c_int64()
+        check(load_library().nl_ctx_mem_info(self._h, C.byref(f), C.byref(t)))
+        return f.value, t.value
 
     @property
     def launch_count(self):

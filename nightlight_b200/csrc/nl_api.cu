@@ -111,6 +111,16 @@ int nl_ctx_device(nl_ctx *ctx, int *device) {
     return NL_OK;
 }
 
+int nl_ctx_mem_info(nl_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes) {
+    NL_REQUIRE(ctx, "ctx is NULL");
+    CtxGuard g(ctx);
+    size_t f = 0, t = 0;
+    NL_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return NL_OK;
+}
+
 int nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches) {
     NL_REQUIRE(ctx && launches, "NULL argument");
     *launches = ctx->launches.load();

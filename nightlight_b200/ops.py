@@ -82,6 +82,40 @@ class OpStack:
         return Image(data=data, naxisn=tuple(frames[0].naxisn), exposure=float(exposure), clip_low=cl, clip_high=ch)
 
 
+def partition(num_frames, width, height, stack_memory_mb, max_threads=1, has_dark=False, has_flat=False, perm=None):
+    """OpStackBatches.partition, stackbatches.go:121-210: frames -> equal batches from a memory budget.
+    -> (order, numBatches, batchSize, maxThreads).  `stack_memory_mb` is the reference's StackMemoryMB; on the
+    GPU pass the device budget (Context.mem_info).  The reference shuffles with math/rand.Perm when there is
+    more than one batch; the permutation is an input here (`perm`, default identity) and each batch's slice
+    of it is sorted ascending like stackbatches.go:196-203."""
+    if num_frames <= 0:
+        raise NightlightError(B.NL_E_INVALID, "No input files to prepare batches")
+    nbytes = int(width) * int(height) * 4
+    available = (int(stack_memory_mb) * 1024 * 1024) // nbytes
+    mt, bs, nb = int(max_threads), 0, 0
+    while mt >= 1:
+        bs = available - mt - (1 if has_dark else 0) - (1 if has_flat else 0)
+        if bs >= 2:
+            nb = (num_frames + bs - 1) // bs
+            if nb > 1:
+                bs -= 2                       # reference frame from batch 0, and the stack of stacks
+            if bs >= 2 and bs >= mt:
+                break
+        mt -= 1
+    if mt < 1 or bs < 2:
+        raise NightlightError(B.NL_E_NOMEM, "Cannot find a stacking execution path within the given memory constraints.")
+    while (bs - 1) * nb >= num_frames:       # even out the size of the last batch
+        bs -= 1
+    order = list(range(num_frames))
+    if nb > 1:
+        order = list(perm) if perm is not None else order
+        if sorted(order) != list(range(num_frames)):
+            raise NightlightError(B.NL_E_INVALID, "perm is not a permutation of the frames")
+        for i in range(nb):
+            order[i * bs:(i + 1) * bs] = sorted(order[i * bs:(i + 1) * bs])
+    return order, nb, bs, mt
+
+
 @dataclass
 class OpStackBatches:
     """The stack-of-stacks arithmetic of OpStackBatches.Apply (stackbatches.go:84-116): every batch is

@@ -91,3 +91,33 @@ def test_stripe_rows_cover_image():
             for (a0, ar), (b0, _) in zip(s, s[1:]):
                 assert a0 + ar == b0
             assert max(r for _, r in s) - min(r for _, r in s) <= 1
+
+
+def test_partition_matches_oracle():
+    """OpStackBatches.partition (stackbatches.go:121-210) host mirror against the oracle's restatement"""
+    import ctypes as C
+    import numpy as np
+    import nightlight_b200 as nl
+    from oracle import oracle as O
+    L = O.lib()
+    L.nlo_partition.restype = C.c_int
+    L.nlo_partition.argtypes = [C.c_int64] * 5 + [C.c_int, C.c_int] + [C.POINTER(C.c_int64)] * 3
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        n = int(rng.integers(1, 5000))
+        w, h = int(rng.integers(100, 9000)), int(rng.integers(100, 9000))
+        mem = int(rng.integers(64, 200000))
+        mt = int(rng.integers(1, 65))
+        dark, flat = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        nb, bs, mo = C.c_int64(), C.c_int64(), C.c_int64()
+        rc = L.nlo_partition(n, w, h, mem, mt, int(dark), int(flat), C.byref(nb), C.byref(bs), C.byref(mo))
+        try:
+            order, gnb, gbs, gmt = nl.partition(n, w, h, mem, mt, dark, flat, perm=list(rng.permutation(n)))
+        except nl.NightlightError as e:
+            assert rc != 0 and "Cannot find a stacking execution path" in str(e)
+            continue
+        assert rc == 0 and (gnb, gbs, gmt) == (nb.value, bs.value, mo.value)
+        assert sorted(order) == list(range(n))
+        for i in range(gnb):
+            chunk = order[i * gbs:(i + 1) * gbs]
+            assert chunk == sorted(chunk)
