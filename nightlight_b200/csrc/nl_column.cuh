@@ -243,6 +243,116 @@ NL_HD float qselect_median(float *a, int n) {
     return nl_mulf(0.5f, nl_addf(lower, upper));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Median by value.  Where only the VALUE of the median matters -- StackMedian (stack.go:274-303) and
+// the median of the absolute deviations in StackMADSigma (stack.go:566-572) -- the permutation the
+// reference's quick-select leaves behind is irrelevant and any exact selection returns the same
+// bits.  This one is built for SIMT: two narrowing levels of REGULAR passes that all 32 lanes run
+// in lock step without divergence, then the flattened quick-select on the few samples that are left.
+// A level sorts 16 evenly spaced samples of the lane's list in registers, picks NP of them around
+// the position where the wanted rank should fall as pivots, counts the list against the pivots
+// (one pass), and compacts the one interval that contains the wanted rank to the front of the
+// buffer (one pass), remembering the largest sample dropped below it (the lower median of an even
+// column may be exactly that one).  The list is destroyed, the result is exact for any data: ties,
+// infinities, lists that do not shrink (all samples equal) just leave more work to the quick-select.
+// ---------------------------------------------------------------------------------------------
+NL_HD void cswap_minmax(float &a, float &b) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo; b = hi;
+}
+
+// bitonic network on 16 registers (ascending); all indices are compile-time constants
+NL_HD void sort16(float (&s)[16]) {
+#pragma unroll
+    for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+        for (int st = k >> 1; st >= 1; st >>= 1) {
+            const bool mirror = st == (k >> 1);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int lo = ((i & ~(st - 1)) << 1) | (i & (st - 1));
+                const int hi = mirror ? (lo ^ (k - 1)) : (lo | st);
+                cswap_minmax(s[lo], s[hi]);
+            }
+        }
+    }
+}
+
+// s[idx] for a run-time idx, -inf / +inf outside 0..15
+NL_HD float pick16(const float (&s)[16], int idx) {
+    float v = idx < 0 ? -INFINITY : INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; j++) v = (idx == j) ? s[j] : v;
+    return v;
+}
+
+// one narrowing level; `go` lanes take part (w > 16), the others pass through untouched
+template <int S, int NP>
+NL_HD void narrow_level(float *g, bool go, int &w, int &r, float &below) {
+    float s[16];
+    const int wl = go ? w : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) s[j] = g[(go ? (int)(((2 * j + 1) * wl) >> 5) : 0) * S];   // centre of the j-th sixteenth
+    sort16(s);
+    const int t = go ? ((r - 1) * 16) / wl : 0;             // sample position of the wanted rank
+    float piv[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) piv[q] = pick16(s, t + 2 * q - (NP - 1));   // NP=2: t-1,t+1;  NP=4: t-3,t-1,t+1,t+3
+    int cnt[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) cnt[q] = 0;
+#pragma unroll 4
+    for (int i = 0; i < wl; i++) {
+        const float v = g[i * S];
+#pragma unroll
+        for (int q = 0; q < NP; q++) cnt[q] += (v < piv[q]) ? 1 : 0;
+    }
+    // the interval [lo, hi) that holds rank r; cb = samples below lo
+    float lo = -INFINITY, hi = INFINITY;
+    int cb = 0;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        if (!found) {
+            if (r <= cnt[q]) { hi = piv[q]; found = true; }
+            else { lo = piv[q]; cb = cnt[q]; }
+        }
+    }
+    // compaction, branch free: four samples are loaded ahead of the stores (the write slot never
+    // overtakes the read slot), every sample is stored at the write slot and the slot only advances
+    // for samples inside the interval
+    int w2 = 0;
+    for (int i = 0; i < wl; i += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = g[(i + u) * S];      // may read up to 3 slots past wl (inside the padded buffer)
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool ok = i + u < wl;
+            const bool lt = v[u] < lo;
+            const bool in = ok & !lt & (!found | (v[u] < hi));   // open-ended last interval: keeps +inf samples
+            below = (ok & lt) ? fmaxf(below, v[u]) : below;
+            if (ok) g[w2 * S] = v[u];                            // (w2 <= i + u: an already consumed slot, or the sample's own)
+            w2 += in ? 1 : 0;
+        }
+    }
+    if (go) { w = w2; r -= cb; }
+}
+
+template <int S, bool GATE = false>
+NL_HD float median_by_value(float *g, int n) {
+    const int k = (n >> 1) + 1;
+    int w = n, r = k;
+    float below = -INFINITY;
+    if (NL_ANY(w > 48)) narrow_level<S, 2>(g, w > 48, w, r, below);
+    if (NL_ANY(w > 48)) narrow_level<S, 4>(g, w > 48, w, r, below);
+    const float upper = qselect<S, GATE>(g, w, r);           // r-th smallest of what is left
+    if (n & 1) return upper;
+    float lower = below;                                      // rank r-1: inside the list, or the largest sample dropped below it
+    for (int i = 0; i < r - 1; i++) lower = fmaxf(lower, g[i * S]);
+    return nl_mulf(0.5f, nl_addf(lower, upper));
+}
+
 // stats.go:246-261 MeanStdDev: two sequential fp32 sums in buffer order, population sigma.
 template <int S>
 NL_HD void mean_stddev(const float *a, int n, float &mean, float &sd) {
@@ -537,7 +647,7 @@ NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi,
     float median = qselect_median<S, (S < 32)>(g, cur);
     for (int i = 0; i < cur; i++) ad[i * S] = fabsf(nl_subf(g[i * S], median));
     if (cur == 0 && S == 32) ad[0] = 0.0f;         // an ungated parked lane compares slot 0 with itself: never a NaN
-    float mad = qselect_median<S, (S < 32)>(ad, cur);
+    float mad = median_by_value<S, (S < 32)>(ad, cur);      // only the value matters: ad is scratch
     float sd = nl_mulf(mad, 1.4826f);
     float lo = nl_subf(median, nl_mulf(sig_lo, sd));
     float hi = nl_addf(median, nl_mulf(sig_hi, sd));

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         __syncwarp();
         float res;
         if (MODE == ST_MEDIAN) {
-            res = qselect_median<S, (S < 32)>(g, cur);                       // stack.go:274-303
+            res = median_by_value<S, (S < 32)>(g, cur);                      // stack.go:274-303
         } else if (MODE == ST_SIGMA) {
             res = reduce_sigma<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else if (MODE == ST_WINSOR) {

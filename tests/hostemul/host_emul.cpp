@@ -42,7 +42,7 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
         }
         if (cur == 0) { res[p] = ref_loc; continue; }
         switch (mode) {
-        case ST_MEDIAN: out = qselect_median<1, true>(g, cur); break;
+        case ST_MEDIAN: out = median_by_value<1, true>(g, cur); break;
         case ST_SIGMA:
             out = W ? reduce_sigma<1, true, unsigned short>(g, gw, weights, cur, sig_lo, sig_hi, ncl, nch)
                     : reduce_sigma<1, false, unsigned short>(g, nullptr, nullptr, cur, sig_lo, sig_hi, ncl, nch);
