@@ -247,8 +247,9 @@ NL_HD float qselect_median(float *a, int n) {
 // Median by value.  Where only the VALUE of the median matters -- StackMedian (stack.go:274-303) and
 // the median of the absolute deviations in StackMADSigma (stack.go:566-572) -- the permutation the
 // reference's quick-select leaves behind is irrelevant and any exact selection returns the same
-// bits.  This one is built for SIMT: two narrowing levels of REGULAR passes that all 32 lanes run
-// in lock step without divergence, then the flattened quick-select on the few samples that are left.
+// bits.  This one is built for SIMT: a narrowing level of REGULAR passes that all 32 lanes run in lock
+// step without divergence (a second level can be enabled; it measured no faster), then the flattened
+// quick-select on the few samples that are left.
 // A level sorts 16 evenly spaced samples of the lane's list in registers, picks NP of them around
 // the position where the wanted rank should fall as pivots, counts the list against the pivots
 // (one pass), and compacts the one interval that contains the wanted rank to the front of the
@@ -344,8 +345,17 @@ NL_HD float median_by_value(float *g, int n) {
     const int k = (n >> 1) + 1;
     int w = n, r = k;
     float below = -INFINITY;
-    if (NL_ANY(w > 48)) narrow_level<S, 2>(g, w > 48, w, r, below);
-    if (NL_ANY(w > 48)) narrow_level<S, 4>(g, w > 48, w, r, below);
+#ifndef NL_MED_NP1
+#define NL_MED_NP1 6
+#endif
+#ifndef NL_MED_NP2
+#define NL_MED_NP2 4
+#endif
+#ifndef NL_MED_T2
+#define NL_MED_T2 0
+#endif
+    if (NL_ANY(w > 48)) narrow_level<S, NL_MED_NP1>(g, w > 48, w, r, below);
+    if (NL_MED_T2 > 0 && NL_ANY(w > NL_MED_T2)) narrow_level<S, NL_MED_NP2>(g, w > NL_MED_T2, w, r, below);
     const float upper = qselect<S, GATE>(g, w, r);           // r-th smallest of what is left
     if (n & 1) return upper;
     float lower = below;                                      // rank r-1: inside the list, or the largest sample dropped below it
