@@ -32,6 +32,3 @@ extern "C" int nlh_fits_write(const char *path, const float *data, const int32_t
         return 0;
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
-extern "C" float nlh_estimate_noise(const float *data, int64_t len, int32_t width) {
-    return EstimateNoise(std::vector<float>(data, data + len), width);
-}

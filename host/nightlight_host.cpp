@@ -265,28 +265,6 @@ float EstimateNoise(Context &c, const std::vector<float> &data, int32_t width) {
     return noise;
 }
 
-float EstimateNoise(const std::vector<float> &data, int32_t width) {
-    static const float w[9] = {1, -2, 1, -2, 4, -2, 1, -2, 1};
-    const int32_t off[9] = {-width - 1, -width, -width + 1, -1, 0, 1, width - 1, width, width + 1};
-    const int32_t height = (int32_t)data.size() / width;
-    float sum = 0;
-    for (int32_t y = 1; y < height - 1; y++) {
-        float rowSum = 0;
-        for (int32_t x = 1; x < width - 1; x++) {
-            const int32_t i = y * width + x;
-            float conv = 0;
-            for (int j = 0; j < 9; j++) {
-                volatile float prod = data[(size_t)(i + off[j])] * w[j];
-                conv += prod;
-            }
-            rowSum += std::fabs(conv);
-        }
-        sum += rowSum;
-    }
-    const float factor = (float)std::sqrt(0.5 * M_PI) / (6 * (float)(width - 2) * (float)(height - 2));
-    return sum * factor;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Stacking
 // ------------------------------------------------------------------------------------------------

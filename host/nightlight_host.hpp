@@ -105,9 +105,7 @@ std::vector<Star> FindStars(Context &c, const std::vector<float> &data, int32_t 
                             float starSig, float bpSigma, float starInOut, int32_t radius, float medianDiffStdDev,
                             float *sumOfShifts, float *avgHFR);
 
-// stats.EstimateNoise, portable definition (noise.go:32-55): on the device, and the same on the host
-// (kept for callers without a context)
+// stats.EstimateNoise, portable definition (noise.go:32-55), computed on the device
 float EstimateNoise(Context &c, const std::vector<float> &data, int32_t width);
-float EstimateNoise(const std::vector<float> &data, int32_t width);
 
 }  // namespace nightlight
