@@ -312,12 +312,12 @@ Image OpStack::Apply(const std::vector<const Image *> &f, Context &c) {
         try {
             size_t lo = rows * g / ndev * width, hi = g + 1 == ndev ? pixels : rows * (g + 1) / ndev * width;
             if (hi <= lo) return;
-            nl_stack_job *job = nullptr;
-            check(nl_stack_begin(c.Device(g), (int32_t)f.size(), (int64_t)(hi - lo), &job));
-            struct End { nl_stack_job *j; ~End() { nl_stack_end(j); } } guard{job};
-            for (size_t i = 0; i < f.size(); i++) check(nl_stack_put_frame(job, (int32_t)i, f[i]->Data.data() + lo, (int64_t)(hi - lo)));
-            check(nl_stack_run(job, mode, weights.empty() ? nullptr : weights.data(), SigmaLow, SigmaHigh, RefFrameLoc,
-                               data.data() + lo, &cl[g], &ch[g]));
+            // all frame pointers of this device's stripe in one call; the library pipelines sub-stripes
+            std::vector<const float *> ptrs(f.size());
+            for (size_t i = 0; i < f.size(); i++) ptrs[i] = f[i]->Data.data() + lo;
+            check(nl_stack_apply(c.Device(g), ptrs.data(), (int32_t)f.size(), (int64_t)(hi - lo), (int64_t)width, 8, mode,
+                                 weights.empty() ? nullptr : weights.data(), SigmaLow, SigmaHigh, RefFrameLoc, data.data() + lo,
+                                 &cl[g], &ch[g]));
         } catch (const std::exception &e) {
             errs[g] = e.what();
         }

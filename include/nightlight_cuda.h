@@ -81,6 +81,13 @@ int  nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_s
  * clip counters (stack.go:140, widened to 64 bit) go to host memory; blocks until they are there. */
 int  nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                   float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
+/* OpStack.Apply in ONE call for hosts that can pass all frame pointers at once: host_frames[i] points to frame
+ * i (pixels floats; pinned memory uploads at full PCIe speed).  The image is cut into n_stripes row stripes
+ * (row_pixels = image width; <= 0: 8 stripes) that alternate on two internal streams, so the upload of one
+ * stripe overlaps the stacking of the previous one; blocks until host_out and the clip counters are filled. */
+int  nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels, int64_t row_pixels,
+                    int32_t n_stripes, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                    float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
 /* Same, result left in device memory (dev_out: pixels floats), asynchronous on the context's stream;
  * the clip counters are readable after nl_ctx_sync via nl_stack_clip_counts. */
 int  nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,

@@ -21,6 +21,7 @@
 #include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through the runtime, libcuda is not linked)
 
 #include <stdlib.h>
+#include <string>
 #include <vector>
 
 namespace nl {
@@ -575,6 +576,70 @@ int nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float si
                                 job->ctx->stream));
     NL_CUDA(cudaStreamSynchronize(job->ctx->stream));
     return nl_stack_clip_counts(job, clip_low, clip_high);
+}
+
+// OpStack.Apply in one call for callers that can hand over all frames at once (C / C++ hosts; a Go host
+// pins the slices and passes a C array of their addresses): the image is cut into row stripes and two
+// internal contexts (streams) alternate, so the upload of stripe s+1 overlaps the stacking of stripe s and
+// the download of stripe s-1 -- the device never holds more than two stripes.
+int nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels, int64_t row_pixels,
+                   int32_t n_stripes, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                   float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
+    NL_REQUIRE(ctx && host_frames && n_frames >= 1 && pixels >= 0, "bad argument");
+    NL_REQUIRE(host_out || pixels == 0, "NULL output");
+    if (clip_low) *clip_low = 0;
+    if (clip_high) *clip_high = 0;
+    if (mode < NL_ST_MEDIAN || mode > NL_ST_AUTO) return set_error(NL_E_INVALID, "invalid stacking mode");
+    if (pixels == 0) return NL_OK;
+    if (row_pixels <= 0 || pixels % row_pixels != 0) row_pixels = pixels;       // no row structure known: one stripe
+    const int64_t rows = pixels / row_pixels;
+    if (n_stripes < 1) n_stripes = 8;
+    if (n_stripes > rows) n_stripes = (int32_t)rows;
+    const int lanes = n_stripes > 1 ? 2 : 1;
+    nl_ctx *lane_ctx[2] = {nullptr, nullptr};
+    nl_stack_job *lane_job[2] = {nullptr, nullptr};
+    float *lane_out[2] = {nullptr, nullptr};
+    int64_t lane_px[2] = {0, 0};
+    int64_t tot_lo = 0, tot_hi = 0;
+    int rc = NL_OK;
+    auto collect = [&](int l) -> int {                      // wait for the lane's stripe and add its clip counts
+        int r = nl_ctx_sync(lane_ctx[l]);
+        if (r != NL_OK) return r;
+        int64_t a = 0, b = 0;
+        r = nl_stack_clip_counts(lane_job[l], &a, &b);
+        tot_lo += a; tot_hi += b;
+        return r;
+    };
+    for (int l = 0; l < lanes && rc == NL_OK; l++) rc = nl_ctx_create(ctx->device, &lane_ctx[l]);
+    for (int32_t si = 0; si < n_stripes && rc == NL_OK; si++) {
+        const int l = si % lanes;
+        const int64_t p0 = rows * si / n_stripes * row_pixels, p1 = rows * (si + 1) / n_stripes * row_pixels, px = p1 - p0;
+        if (si >= lanes) rc = collect(l);
+        if (rc == NL_OK && px != lane_px[l]) {               // (re)size the lane for this stripe
+            if (lane_job[l]) { nl_stack_end(lane_job[l]); lane_job[l] = nullptr; }
+            if (lane_out[l]) { nl_dev_free(lane_ctx[l], lane_out[l]); lane_out[l] = nullptr; }
+            rc = nl_stack_begin(lane_ctx[l], n_frames, px, &lane_job[l]);
+            if (rc == NL_OK) rc = nl_dev_alloc(lane_ctx[l], 4 * px, (void **)&lane_out[l]);
+            lane_px[l] = px;
+        }
+        for (int32_t k = 0; k < n_frames && rc == NL_OK; k++) {
+            if (!host_frames[k]) rc = set_error(NL_E_INVALID, "frame %d is NULL", k);
+            else rc = nl_stack_put_frame(lane_job[l], k, host_frames[k] + p0, px);
+        }
+        if (rc == NL_OK) rc = nl_stack_run_dev(lane_job[l], mode, weights, sigma_low, sigma_high, ref_frame_loc, lane_out[l]);
+        if (rc == NL_OK) rc = nl_memcpy_d2h(lane_ctx[l], host_out + p0, lane_out[l], 4 * px);
+    }
+    for (int l = 0; l < lanes && l < n_stripes && rc == NL_OK; l++) rc = collect(l);
+    std::string err = rc == NL_OK ? std::string() : std::string(nl_last_error());
+    for (int l = 0; l < 2; l++) {
+        if (lane_job[l]) nl_stack_end(lane_job[l]);
+        if (lane_out[l]) nl_dev_free(lane_ctx[l], lane_out[l]);
+        if (lane_ctx[l]) nl_ctx_destroy(lane_ctx[l]);
+    }
+    if (rc != NL_OK) return set_error(rc, "%s", err.c_str());
+    if (clip_low) *clip_low = tot_lo;
+    if (clip_high) *clip_high = tot_hi;
+    return NL_OK;
 }
 
 int nl_stack_end(nl_stack_job *job) {

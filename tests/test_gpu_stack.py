@@ -250,3 +250,26 @@ def test_infinities_denormals_and_huge_values(ctx):
     frames[::2, 230:240] = 0.0
     for mode, weighted in mode_cases():
         check_against_oracle(ctx, frames, mode, weighted)
+
+
+def test_stack_apply_one_call_striped(ctx):
+    """nl_stack_apply: all host frame pointers in one call, stripes pipelined inside the library"""
+    import ctypes as C
+    lib = nl.load_library()
+    w, h, n = 64, 37, 20                           # 37 rows: ragged stripes
+    frames = O.synth_frames(n, 4242, w * h)
+    ptrs = (C.c_void_p * n)(*[frames[i].ctypes.data for i in range(n)])
+    wts = weights_for(n)
+    for stripes in (1, 3, 8, 100):
+        for mode, name, wv in ((nl.ST_SIGMA, "sigma", None), (nl.ST_WINSOR_SIGMA, "winsor", wts), (nl.ST_AUTO, "winsor", None)):
+            out = np.empty(w * h, np.float32)
+            cl, ch = C.c_int64(), C.c_int64()
+            wp = wv.ctypes.data_as(C.POINTER(C.c_float)) if wv is not None else None
+            nl.binding.check(lib.nl_stack_apply(ctx.handle, ptrs, n, w * h, w, stripes, mode, wp, 2.75, 2.75, 0.0,
+                                                out.ctypes.data_as(C.c_void_p), C.byref(cl), C.byref(ch)))
+            want = O.stack(frames, name, weights=wv)
+            assert bits_equal(out, want[0]), (stripes, name)
+            assert (cl.value, ch.value) == want[1:]
+    out = np.empty(w * h, np.float32)
+    rc = lib.nl_stack_apply(ctx.handle, ptrs, n, w * h, w, 2, 9, None, 2.75, 2.75, 0.0, out.ctypes.data_as(C.c_void_p), None, None)
+    assert rc == nl.binding.NL_E_INVALID and b"invalid stacking mode" in lib.nl_last_error()
