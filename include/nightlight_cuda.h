@@ -88,6 +88,9 @@ int  nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float s
 int  nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels, int64_t row_pixels,
                     int32_t n_stripes, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                     float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
+/* nl_stack_apply keeps its two stripe lanes (device buffers of 2 x n_frames x stripe pixels) in the context
+ * between calls; this frees them early (nl_ctx_destroy does it too). */
+int  nl_stack_apply_release(nl_ctx *ctx);
 /* Same, result left in device memory (dev_out: pixels floats), asynchronous on the context's stream;
  * the clip counters are readable after nl_ctx_sync via nl_stack_clip_counts. */
 int  nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,

@@ -51,6 +51,7 @@ DECLARED_SYMBOLS = {
     "nl_stack_run": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp, _i64p, _i64p]),
     "nl_stack_apply": (C.c_int, [_vp, C.POINTER(_vp), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float,
                                  C.c_float, _vp, _i64p, _i64p]),
+    "nl_stack_apply_release": (C.c_int, [_vp]),
     "nl_stack_run_dev": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp]),
     "nl_stack_run_dev_bcast": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(_vp), C.c_int32]),
     "nl_stack_clip_counts": (C.c_int, [_vp, _i64p, _i64p]),

@@ -83,6 +83,7 @@ int nl_ctx_create(int device, nl_ctx **out) {
 
 int nl_ctx_destroy(nl_ctx *ctx) {
     if (!ctx) return NL_OK;
+    nl_stack_apply_release(ctx);
     CtxGuard g(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);

@@ -23,6 +23,13 @@ struct nl_ctx {
     size_t scratch_bytes = 0;
     void *list = nullptr;            // candidate list of the star scan (kept apart from `scratch`, which holds the row offsets)
     size_t list_bytes = 0;
+    // nl_stack_apply keeps its two stripe lanes (context + job + result buffer each) between calls:
+    // allocating and freeing multi-GiB device buffers per call would cost more than the stack itself
+    nl_ctx *lane_ctx[2] = {nullptr, nullptr};
+    struct nl_stack_job *lane_job[2] = {nullptr, nullptr};
+    float *lane_out[2] = {nullptr, nullptr};
+    int64_t lane_px[2] = {0, 0};
+    int lane_frames[2] = {0, 0};
 };
 
 namespace nl {

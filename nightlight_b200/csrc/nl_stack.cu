@@ -596,49 +596,59 @@ int nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frame
     if (n_stripes < 1) n_stripes = 8;
     if (n_stripes > rows) n_stripes = (int32_t)rows;
     const int lanes = n_stripes > 1 ? 2 : 1;
-    nl_ctx *lane_ctx[2] = {nullptr, nullptr};
-    nl_stack_job *lane_job[2] = {nullptr, nullptr};
-    float *lane_out[2] = {nullptr, nullptr};
-    int64_t lane_px[2] = {0, 0};
     int64_t tot_lo = 0, tot_hi = 0;
     int rc = NL_OK;
     auto collect = [&](int l) -> int {                      // wait for the lane's stripe and add its clip counts
-        int r = nl_ctx_sync(lane_ctx[l]);
+        int r = nl_ctx_sync(ctx->lane_ctx[l]);
         if (r != NL_OK) return r;
         int64_t a = 0, b = 0;
-        r = nl_stack_clip_counts(lane_job[l], &a, &b);
+        r = nl_stack_clip_counts(ctx->lane_job[l], &a, &b);
         tot_lo += a; tot_hi += b;
         return r;
     };
-    for (int l = 0; l < lanes && rc == NL_OK; l++) rc = nl_ctx_create(ctx->device, &lane_ctx[l]);
+    for (int l = 0; l < lanes && rc == NL_OK; l++)
+        if (!ctx->lane_ctx[l]) rc = nl_ctx_create(ctx->device, &ctx->lane_ctx[l]);
     for (int32_t si = 0; si < n_stripes && rc == NL_OK; si++) {
         const int l = si % lanes;
         const int64_t p0 = rows * si / n_stripes * row_pixels, p1 = rows * (si + 1) / n_stripes * row_pixels, px = p1 - p0;
         if (si >= lanes) rc = collect(l);
-        if (rc == NL_OK && px != lane_px[l]) {               // (re)size the lane for this stripe
-            if (lane_job[l]) { nl_stack_end(lane_job[l]); lane_job[l] = nullptr; }
-            if (lane_out[l]) { nl_dev_free(lane_ctx[l], lane_out[l]); lane_out[l] = nullptr; }
-            rc = nl_stack_begin(lane_ctx[l], n_frames, px, &lane_job[l]);
-            if (rc == NL_OK) rc = nl_dev_alloc(lane_ctx[l], 4 * px, (void **)&lane_out[l]);
-            lane_px[l] = px;
+        if (rc == NL_OK && (px != ctx->lane_px[l] || n_frames != ctx->lane_frames[l] || !ctx->lane_job[l])) {   // (re)size the lane
+            if (ctx->lane_job[l]) { nl_stack_end(ctx->lane_job[l]); ctx->lane_job[l] = nullptr; }
+            if (ctx->lane_out[l]) { nl_dev_free(ctx->lane_ctx[l], ctx->lane_out[l]); ctx->lane_out[l] = nullptr; }
+            ctx->lane_px[l] = 0;
+            rc = nl_stack_begin(ctx->lane_ctx[l], n_frames, px, &ctx->lane_job[l]);
+            if (rc == NL_OK) rc = nl_dev_alloc(ctx->lane_ctx[l], 4 * px, (void **)&ctx->lane_out[l]);
+            if (rc == NL_OK) { ctx->lane_px[l] = px; ctx->lane_frames[l] = n_frames; }
         }
         for (int32_t k = 0; k < n_frames && rc == NL_OK; k++) {
             if (!host_frames[k]) rc = set_error(NL_E_INVALID, "frame %d is NULL", k);
-            else rc = nl_stack_put_frame(lane_job[l], k, host_frames[k] + p0, px);
+            else rc = nl_stack_put_frame(ctx->lane_job[l], k, host_frames[k] + p0, px);
         }
-        if (rc == NL_OK) rc = nl_stack_run_dev(lane_job[l], mode, weights, sigma_low, sigma_high, ref_frame_loc, lane_out[l]);
-        if (rc == NL_OK) rc = nl_memcpy_d2h(lane_ctx[l], host_out + p0, lane_out[l], 4 * px);
+        if (rc == NL_OK)
+            rc = nl_stack_run_dev(ctx->lane_job[l], mode, weights, sigma_low, sigma_high, ref_frame_loc, ctx->lane_out[l]);
+        if (rc == NL_OK) rc = nl_memcpy_d2h(ctx->lane_ctx[l], host_out + p0, ctx->lane_out[l], 4 * px);
     }
     for (int l = 0; l < lanes && l < n_stripes && rc == NL_OK; l++) rc = collect(l);
-    std::string err = rc == NL_OK ? std::string() : std::string(nl_last_error());
-    for (int l = 0; l < 2; l++) {
-        if (lane_job[l]) nl_stack_end(lane_job[l]);
-        if (lane_out[l]) nl_dev_free(lane_ctx[l], lane_out[l]);
-        if (lane_ctx[l]) nl_ctx_destroy(lane_ctx[l]);
+    if (rc != NL_OK) {                                       // leave no copy in flight from or to the caller's buffers
+        std::string err = nl_last_error();
+        for (int l = 0; l < 2; l++)
+            if (ctx->lane_ctx[l]) nl_ctx_sync(ctx->lane_ctx[l]);
+        return set_error(rc, "%s", err.c_str());
     }
-    if (rc != NL_OK) return set_error(rc, "%s", err.c_str());
     if (clip_low) *clip_low = tot_lo;
     if (clip_high) *clip_high = tot_hi;
+    return NL_OK;
+}
+
+// releases the stripe lanes nl_stack_apply keeps between calls (also done by nl_ctx_destroy)
+int nl_stack_apply_release(nl_ctx *ctx) {
+    NL_REQUIRE(ctx, "ctx is NULL");
+    for (int l = 0; l < 2; l++) {
+        if (ctx->lane_job[l]) { nl_stack_end(ctx->lane_job[l]); ctx->lane_job[l] = nullptr; }
+        if (ctx->lane_out[l]) { nl_dev_free(ctx->lane_ctx[l], ctx->lane_out[l]); ctx->lane_out[l] = nullptr; }
+        if (ctx->lane_ctx[l]) { nl_ctx_destroy(ctx->lane_ctx[l]); ctx->lane_ctx[l] = nullptr; }
+        ctx->lane_px[l] = 0; ctx->lane_frames[l] = 0;
+    }
     return NL_OK;
 }
 
