@@ -273,3 +273,25 @@ def test_stack_apply_one_call_striped(ctx):
     out = np.empty(w * h, np.float32)
     rc = lib.nl_stack_apply(ctx.handle, ptrs, n, w * h, w, 2, 9, None, 2.75, 2.75, 0.0, out.ctypes.data_as(C.c_void_p), None, None)
     assert rc == nl.binding.NL_E_INVALID and b"invalid stacking mode" in lib.nl_last_error()
+
+
+def test_random_shapes_and_modes_fuzz(ctx):
+    """seeded fuzz over frame counts, pixel counts (ragged tiles, unaligned rows -> both staging paths),
+    NaN densities, outliers, sigmas and modes: every result bit-identical to the oracle"""
+    rng = np.random.default_rng(20261017)
+    cases = mode_cases()
+    for it in range(60):
+        n = int(rng.choice([2, 3, 4, 7, 9, 14, 17, 24, 26, 31, 33, 48, 65, 127, 129, 200, 255, 256, 257, 300]))
+        p = int(rng.integers(1, 700))
+        scale = float(rng.choice([1e-3, 1.0, 50.0, 4e4]))
+        frames = (rng.standard_normal((n, p)) * scale + float(rng.choice([0.0, 1000.0, -3.0]))).astype(np.float32)
+        if rng.random() < 0.7:
+            frames[rng.random(frames.shape) < float(rng.choice([0.001, 0.02, 0.3]))] = np.nan
+        if rng.random() < 0.7:
+            frames[rng.random(frames.shape) < 0.03] += np.float32(20 * scale)
+        if rng.random() < 0.3:
+            frames = np.round(frames).astype(np.float32)          # ties
+        sl, sh = (float(x) for x in rng.choice([0.5, 1.0, 2.0, 2.75, 4.0, -1.0], 2))
+        mode, weighted = cases[int(rng.integers(0, len(cases)))]
+        w = (rng.random(n).astype(np.float32) + np.float32(0.05)) if weighted else None
+        check_against_oracle(ctx, frames, mode, weighted, sl, sh, ref_loc=float(rng.choice([0.0, 7.5])), w=w)
