@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         const long long p = t * S + lane;
         const bool valid = lane < S && p < a.pixels;
         int cur = 0;
+        bool negzero = false;            // median mode: a -0.0 sample makes the SIGN of a zero median depend on the permutation
         if (tma_tiles) {
             // (the slab was last touched by this warp's generic-proxy loads and stores: order them
             // before the async-proxy writes of the tensor copies)
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
                 const float v = g[k * S];
                 if (cur != k) g[cur * S] = v;
                 if (W) gw[cur * S] = (IDX)k;
+                if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v) == 0x80000000u;
                 cur += (v == v) ? 1 : 0;
             }
         } else if (valid) {
@@ -208,11 +210,13 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
                 for (int u = 0; u < 32; u++) {
                     g[cur * S] = v[u];
                     if (W) gw[cur * S] = (IDX)(k + u);
+                    if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v[u]) == 0x80000000u;
                     cur += (v[u] == v[u]) ? 1 : 0;
                 }
             }
             for (; k < n; k++) {
                 float v = ld_stream(src + (long long)k * a.stride);
+                if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v) == 0x80000000u;
                 if (v == v) {
                     g[cur * S] = v;
                     if (W) gw[cur * S] = (IDX)k;
@@ -224,7 +228,11 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         __syncwarp();
         float res;
         if (MODE == ST_MEDIAN) {
-            res = median_by_value<S, (S < 32)>(g, cur);                      // stack.go:274-303
+            // stack.go:274-303.  Only the value of the median matters -- except for the sign of a zero: with
+            // both -0.0 and +0.0 among the samples the reference's result carries the sign its permutation
+            // happens to leave at the median slot, so such (rare) tiles take the emulated quick-select.
+            if (__any_sync(0xffffffffu, negzero)) res = qselect_median<S, (S < 32)>(g, cur);
+            else res = median_by_value<S, (S < 32)>(g, cur);
         } else if (MODE == ST_SIGMA) {
             res = reduce_sigma<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else if (MODE == ST_WINSOR) {

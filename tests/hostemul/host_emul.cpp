@@ -2,6 +2,7 @@
 // routines, __host__ __device__) for the CPU with element stride S = 1, so the "not gpu" tests can
 // compare the exact code the kernels run against the oracle without a GPU.  Test infrastructure.
 #include "../../nightlight_b200/csrc/nl_column.cuh"
+#include <cmath>
 #include <vector>
 #include <cstddef>
 
@@ -42,7 +43,12 @@ extern "C" int emul_stack(int mode, const float *const *lights, int n, size_t le
         }
         if (cur == 0) { res[p] = ref_loc; continue; }
         switch (mode) {
-        case ST_MEDIAN: out = median_by_value<1, true>(g, cur); break;
+        case ST_MEDIAN: {          // like the kernel: a -0.0 sample sends the column to the emulated quick-select
+            bool negzero = false;
+            for (int i = 0; i < cur; i++) negzero |= (g[i] == 0.0f && std::signbit(g[i]));
+            out = negzero ? qselect_median<1, true>(g, cur) : median_by_value<1, true>(g, cur);
+            break;
+        }
         case ST_SIGMA:
             out = W ? reduce_sigma<1, true, unsigned short>(g, gw, weights, cur, sig_lo, sig_hi, ncl, nch)
                     : reduce_sigma<1, false, unsigned short>(g, nullptr, nullptr, cur, sig_lo, sig_hi, ncl, nch);

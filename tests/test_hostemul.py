@@ -85,3 +85,29 @@ def test_reducers_random_data_and_sigmas(hostemul):
                 b = emul_stack(hostemul, frames, mode, sl, sh, w if weighted else None, ref_loc=0.25)
                 assert bits_equal(a[0], b[0]), (n, sl, mode, weighted, first_mismatch(a[0], b[0]))
                 assert a[1:] == b[1:], (n, sl, mode, weighted)
+
+
+def test_fuzz_shapes_modes_signed_zeros(hostemul):
+    """seeded fuzz (the same generator as the GPU fuzz test): frame counts, NaN densities, outliers, ties
+    including -0.0 / +0.0 mixes, negative sigmas, every mode -- device routines (host build) == oracle"""
+    rng = np.random.default_rng(20261017)
+    cases = mode_cases()
+    for it in range(60):
+        n = int(rng.choice([2, 3, 4, 7, 9, 14, 17, 24, 26, 31, 33, 48, 65, 127, 129, 200, 255, 256, 257, 300]))
+        p = int(rng.integers(1, 700))
+        scale = float(rng.choice([1e-3, 1.0, 50.0, 4e4]))
+        frames = (rng.standard_normal((n, p)) * scale + float(rng.choice([0.0, 1000.0, -3.0]))).astype(np.float32)
+        if rng.random() < 0.7:
+            frames[rng.random(frames.shape) < float(rng.choice([0.001, 0.02, 0.3]))] = np.nan
+        if rng.random() < 0.7:
+            frames[rng.random(frames.shape) < 0.03] += np.float32(20 * scale)
+        if rng.random() < 0.3:
+            frames = np.round(frames).astype(np.float32)
+        sl, sh = (float(x) for x in rng.choice([0.5, 1.0, 2.0, 2.75, 4.0, -1.0], 2))
+        mode, weighted = cases[int(rng.integers(0, len(cases)))]
+        w = (rng.random(n).astype(np.float32) + np.float32(0.05)) if weighted else None
+        ref = float(rng.choice([0.0, 7.5]))
+        want = O.stack(frames, mode, sl, sh, weights=w, ref_loc=ref)
+        got = emul_stack(hostemul, frames, mode, sl, sh, w, ref)
+        assert bits_equal(got[0], want[0]), (it, n, p, mode, weighted, sl, sh, first_mismatch(got[0], want[0]))
+        assert got[1:] == want[1:], (it, mode, got[1:], want[1:])
