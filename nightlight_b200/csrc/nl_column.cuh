@@ -239,7 +239,10 @@ NL_HD float qselect_median(float *a, int n) {
     float upper = qselect<S, GATE>(a, n, k);
     if (n & 1) return upper;
     float lower = a[0];
-    for (int i = 1; i < k - 1; i++) lower = fmaxf(lower, a[i * S]);   // no NaNs in a column
+    for (int i = 1; i < k - 1; i++) {          // `if a[i]>lower { lower=a[i] }`: a comparison, not fmaxf -- it keeps
+        const float v = a[i * S];              // the FIRST of equal values, which decides between -0.0 and +0.0
+        lower = v > lower ? v : lower;
+    }
     return nl_mulf(0.5f, nl_addf(lower, upper));
 }
 
