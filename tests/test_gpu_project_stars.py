@@ -214,3 +214,35 @@ def test_stack_from_raw_int16_payloads(ctx):
         got = job.run(nl.ST_SIGMA)
     want = O.stack(frames, "sigma")
     assert bits_equal(got[0], want[0]) and got[1:] == want[1:]
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_project_and_bright_scan_fuzz(ctx, seed):
+    """seeded fuzz: image sizes, affine transforms (rotation, scale, shear, large shifts), fill values; star
+    scan thresholds and radii on images with plateaus -- bit-identical to the oracle"""
+    rng = np.random.default_rng(seed)
+    for it in range(25):
+        sw, sh = int(rng.integers(1, 200)), int(rng.integers(1, 150))
+        dw, dh = int(rng.integers(1, 200)), int(rng.integers(1, 150))
+        src = (rng.standard_normal(sw * sh) * 30 + 500).astype(np.float32)
+        th = np.deg2rad(rng.uniform(-180, 180))
+        sc = rng.uniform(0.3, 3.0)
+        trans = np.array([sc * np.cos(th), -sc * np.sin(th) + rng.uniform(-0.2, 0.2), rng.uniform(-sw, sw),
+                          sc * np.sin(th), sc * np.cos(th), rng.uniform(-sh, sh)], np.float32)
+        oob = np.float32(rng.choice([np.nan, 0.0, -1.5]))
+        try:
+            want = O.project(src, sw, sh, dw, dh, trans, oob)
+        except Exception:
+            with pytest.raises(nl.NightlightError):
+                nl.project(ctx, src, sw, sh, dw, dh, trans, oob)
+            continue
+        got = nl.project(ctx, src, sw, sh, dw, dh, trans, oob)
+        assert bits_equal(got, want), (it, sw, sh, dw, dh, list(trans), first_mismatch(got, want))
+    for it in range(25):
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 60))
+        img = np.round(rng.standard_normal(w * h) * 2 + 10).astype(np.float32)       # many equal values: plateaus
+        thr = float(rng.choice([9.5, 11.5, 13.5, 100.0]))
+        radius = int(rng.choice([0, 1, 2, 5, 16, 500]))
+        got = nl.find_bright_pixels(ctx, img, w, thr, radius)
+        want = O.find_bright_pixels(img, w, thr, radius)
+        assert got.tobytes() == want.tobytes(), (it, w, h, thr, radius)
