@@ -90,6 +90,19 @@ def test_ties_and_integers(ctx):
         check_against_oracle(ctx, frames, mode, weighted)
 
 
+@pytest.mark.parametrize("n", [7, 16, 40, 256])
+def test_signed_zero_ties_every_mode(ctx, n):
+    """columns made of -1, -0.0, +0.0, 1 with both zero signs straddling the median: the sign of a zero result
+    depends on the reference's permutation and on `>` (not fmax) keeping the first of equal values"""
+    rng = np.random.default_rng(100 + n)
+    frames = np.round(rng.standard_normal((n, 900)) * 0.6).astype(np.float32)
+    assert (np.signbit(frames) & (frames == 0)).any() and ((~np.signbit(frames)) & (frames == 0)).any()
+    frames[rng.random(frames.shape) < 0.02] = np.nan
+    for mode, weighted in mode_cases():
+        for sl, sh in ((2.75, 2.75), (0.5, 1.0)):
+            check_against_oracle(ctx, frames, mode, weighted, sl, sh)
+
+
 def test_many_frames_small_tile_path(ctx):
     """n_frames beyond what fits 32 pixel columns per warp in shared memory (narrower tile kernels)"""
     frames = O.synth_frames(2000, 99, 70)

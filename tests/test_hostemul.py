@@ -87,6 +87,20 @@ def test_reducers_random_data_and_sigmas(hostemul):
                 assert a[1:] == b[1:], (n, sl, mode, weighted)
 
 
+@pytest.mark.parametrize("n", [7, 16, 40, 256])
+def test_signed_zero_ties_every_mode(hostemul, n):
+    rng = np.random.default_rng(100 + n)
+    frames = np.round(rng.standard_normal((n, 900)) * 0.6).astype(np.float32)
+    frames[rng.random(frames.shape) < 0.02] = np.nan
+    for mode, weighted in mode_cases():
+        w = weights_for(n) if weighted else None
+        for sl, sh in ((2.75, 2.75), (0.5, 1.0)):
+            a = O.stack(frames, mode, sl, sh, weights=w)
+            b = emul_stack(hostemul, frames, mode, sl, sh, w)
+            assert bits_equal(a[0], b[0]), (n, mode, weighted, sl, first_mismatch(a[0], b[0]))
+            assert a[1:] == b[1:]
+
+
 @pytest.mark.parametrize("seed", [20261017, 1, 2, 3])
 def test_fuzz_shapes_modes_signed_zeros(hostemul, seed):
     """seeded fuzz (the same generator as the GPU fuzz test): frame counts, NaN densities, outliers, ties
