@@ -246,3 +246,23 @@ def test_project_and_bright_scan_fuzz(ctx, seed):
         got = nl.find_bright_pixels(ctx, img, w, thr, radius)
         want = O.find_bright_pixels(img, w, thr, radius)
         assert got.tobytes() == want.tobytes(), (it, w, h, thr, radius)
+
+
+def test_find_stars_fuzz(ctx):
+    """seeded fuzz of the whole FindStars pipeline: field sizes, star densities, detection sigmas, radii,
+    in/out ratios, with and without the bad-pixel rejection"""
+    rng = np.random.default_rng(77)
+    for it in range(8):
+        w, h = int(rng.integers(200, 900)), int(rng.integers(150, 600))
+        img = star_field(w, h, int(rng.integers(5, w * h // 3000 + 6)), seed=int(rng.integers(0, 10**6)),
+                         noise=float(rng.uniform(1, 5)), hot=int(rng.integers(0, 30)))
+        loc, scale = 100.0, float(rng.uniform(1.0, 5.0))
+        star_sig = float(rng.choice([5.0, 10.0, 15.0, 25.0]))
+        radius = int(rng.choice([4, 8, 16, 24]))
+        in_out = float(rng.choice([1.0, 1.4, 2.0]))
+        bp_sigma, md_sd = (0.0, 0.0) if rng.random() < 0.5 else (float(rng.choice([3.0, 5.0])), float(rng.uniform(1, 6)))
+        got = nl.find_stars(ctx, img, w, loc, scale, star_sig, bp_sigma, in_out, radius, md_sd)
+        want = O.find_stars(img, w, loc, scale, star_sig, bp_sigma, in_out, radius, md_sd)
+        assert len(got[0]) == len(want[0]), (it, len(got[0]), len(want[0]))
+        assert got[0].tobytes() == want[0].tobytes(), it
+        assert bits_equal([got[1], got[2]], [want[1], want[2]]), it
