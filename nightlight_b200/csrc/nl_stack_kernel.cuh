@@ -1,0 +1,298 @@
+// nl_stack_kernel.cuh -- the column kernel of the order-statistics stacking modes and its launcher, shared by
+// the per-mode translation units (nl_stack_sigma.cu, nl_stack_winsor.cu, nl_stack_linfit.cu: one object file per
+// mode family keeps the build parallel) and by nl_stack.cu (job API, mean kernels, dispatch).
+#pragma once
+
+#include "nl_internal.h"
+#include "nl_column.cuh"
+
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through the runtime, libcuda is not linked)
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+namespace nl {
+
+struct StackArgs {
+    const float *frames;     // [n][stride]
+    long long stride;        // elements between frames
+    long long pixels;
+    int n;
+    const float *weights;    // [n] or nullptr
+    const float *ramp;       // [2*(n+1)] MeanStdDev of 0..c-1, linear fit only
+    float ref_loc, sig_lo, sig_hi;
+    float *out;              // [pixels]
+    int use_tma;             // tiles are staged by TMA tensor copies (16-byte aligned frame rows)
+    float *peer_out[NL_MAX_PEERS];   // further copies of the result (peer-mapped stripes of the gathered image)
+    int n_peers;
+    unsigned long long *clip;   // [2] low, high
+    unsigned long long *tile_counter;   // next tile of the dynamic scheduler (zeroed per launch)
+};
+
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+
+// ---- TMA staging of a tile: the frame stack is described by a 2-D tensor map [frame][pixel]; one
+// tensor copy moves a [32 frames x 32 pixels] box (32 rows of 128 bytes) straight from HBM/L2 into
+// the warp's [sample][lane] slab in shared memory, N/32 boxes per tile, all in flight at once and
+// completing on the warp's mbarrier.  Out-of-range pixels and frames arrive as NaN (the map's fill
+// mode), which is exactly "no sample" for the reducers.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mb, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+    return ok != 0;
+}
+// one [TMA_ROWS frames x 32 pixels] box of the frame stack -> shared memory (SASS: UTMALDG)
+constexpr int TMA_ROWS = 32;
+__device__ __forceinline__ void tma_box_g2s(unsigned dst, const CUtensorMap *tmap, int pixel0, int frame0, unsigned mb) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(pixel0), "r"(frame0), "r"(mb) : "memory");
+}
+
+// Result store.  Multi-GPU: the reassembly of the stacked image is fused into this epilogue -- besides
+// the local copy, every warp stores its 128-byte result segment straight into the gathered image of
+// each peer GPU (peer-mapped memory over NVLink), so no separate all-gather pass runs afterwards.
+__device__ __forceinline__ void store_result(const StackArgs &a, long long p, float v) {
+    a.out[p] = v;
+    for (int e = 0; e < a.n_peers; e++) a.peer_out[e][p] = v;
+}
+
+// ---- order-statistics modes ------------------------------------------------------------------
+// shared-memory bytes per column slot: the fp32 samples, the MAD scratch column, and (weighted
+// modes) the frame index of every sample
+template <int MODE, bool W, typename IDX> struct SlotBytes {
+    static constexpr int value = 4 * (MODE == ST_MAD ? 2 : 1) + (W ? (int)sizeof(IDX) : 0);
+};
+
+template <int MODE, bool W, int S, typename IDX>
+__global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n = a.n;
+    const int npad = (n + 31) & ~31;                              // clip_pass scans whole 32-slot blocks
+    constexpr int SB = SlotBytes<MODE, W, IDX>::value;
+    // column element i of this lane's pixel at g[i*S]; lanes beyond a narrow tile alias a valid
+    // column but never get samples (cur = 0) and never store
+    // (a gap of QW-1 rows in front of, between and behind the warp slabs: the quick-select windows may
+    // read, never use, up to QW-1 slots outside a column -- they land in a gap nobody writes, never in
+    // another warp's live data)
+    constexpr size_t GAP = (size_t)(QW - 1) * S * 4;
+    const size_t slab_bytes = (size_t)SB * S * npad;
+    char *region = reinterpret_cast<char *>(smem) + GAP + (size_t)warp * (slab_bytes + GAP);
+    float *g = reinterpret_cast<float *>(region) + (lane % S);
+    float *sc = g + (size_t)S * npad;                             // MAD scratch column
+    IDX *gw = reinterpret_cast<IDX *>(region + (size_t)4 * (MODE == ST_MAD ? 2 : 1) * S * npad) + (lane % S);
+    (void)sc; (void)gw;
+
+    const long long tiles = (a.pixels + S - 1) / S;
+    int ncl = 0, nch = 0;
+
+    // one mbarrier per warp for the TMA staging, in the last 64 bytes of the last gap (32-pixel tiles only:
+    // at N = 256 the seven slabs and eight gaps fill the 232 448 bytes a CTA may use to the byte; a window
+    // load of the last warp that strays there reads the barrier words as meaningless sample data)
+    const unsigned mb = smem_u32(reinterpret_cast<char *>(smem) + GAP + (size_t)(blockDim.x >> 5) * (slab_bytes + GAP) - 64) + 8u * warp;
+    const bool tma_tiles = S == 32 && a.use_tma;
+    unsigned tma_phase = 0;
+    if (tma_tiles) {
+        if (lane == 0) mbar_init(mb, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // make the init visible to the async proxy
+        __syncwarp();
+    }
+
+    // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles from a counter
+    auto next_tile = [&]() {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(a.tile_counter, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    for (long long t = next_tile(); t < tiles; t = next_tile()) {
+        const long long p = t * S + lane;
+        const bool valid = lane < S && p < a.pixels;
+        int cur = 0;
+        bool negzero = false;            // median mode: a -0.0 sample makes the SIGN of a zero median depend on the permutation
+        if (tma_tiles) {
+            // (the slab was last touched by this warp's generic-proxy loads and stores: order them
+            // before the async-proxy writes of the tensor copies)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(mb, (unsigned)npad * (S * 4));
+            __syncwarp();
+            const unsigned slab = smem_u32(region);
+            for (int j = lane; j * TMA_ROWS < npad; j += 32)
+                tma_box_g2s(slab + (unsigned)j * (TMA_ROWS * S * 4), &tmap, (int)(t * S), j * TMA_ROWS, mb);
+            while (!mbar_try_wait(mb, tma_phase)) {}
+            tma_phase ^= 1;
+            // drop the NaNs in frame order, in place (stack.go:380-387); nothing moves until the first NaN
+#pragma unroll 8
+            for (int k = 0; k < n; k++) {
+                const float v = g[k * S];
+                if (cur != k) g[cur * S] = v;
+                if (W) gw[cur * S] = (IDX)k;
+                if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v) == 0x80000000u;
+                cur += (v == v) ? 1 : 0;
+            }
+        } else if (valid) {
+            // unaligned frame rows or narrow tiles: gather the non-NaN samples through registers, 32 loads
+            // in flight per lane, each a 128-byte row segment per warp
+            const float *src = a.frames + p;
+            int k = 0;
+            for (; k + 32 <= n; k += 32) {
+                float v[32];
+#pragma unroll
+                for (int u = 0; u < 32; u++) v[u] = ld_stream(src + (long long)(k + u) * a.stride);
+#pragma unroll
+                for (int u = 0; u < 32; u++) {
+                    g[cur * S] = v[u];
+                    if (W) gw[cur * S] = (IDX)(k + u);
+                    if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v[u]) == 0x80000000u;
+                    cur += (v[u] == v[u]) ? 1 : 0;
+                }
+            }
+            for (; k < n; k++) {
+                float v = ld_stream(src + (long long)k * a.stride);
+                if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v) == 0x80000000u;
+                if (v == v) {
+                    g[cur * S] = v;
+                    if (W) gw[cur * S] = (IDX)k;
+                    cur++;
+                }
+            }
+        }
+        if (cur == 0 && lane < S) g[0] = 0.0f;                    // parked lanes compare slot 0 with itself
+        __syncwarp();
+        float res;
+        if (MODE == ST_MEDIAN) {
+            // stack.go:274-303.  Only the value of the median matters -- except for the sign of a zero: with
+            // both -0.0 and +0.0 among the samples the reference's result carries the sign its permutation
+            // happens to leave at the median slot, so such (rare) tiles take the emulated quick-select.
+            if (__any_sync(0xffffffffu, negzero)) res = qselect_median<S, (S < 32)>(g, cur);
+            else res = median_by_value<S, (S < 32)>(g, cur);
+        } else if (MODE == ST_SIGMA) {
+            res = reduce_sigma<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else if (MODE == ST_WINSOR) {
+            res = reduce_winsor<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else if (MODE == ST_MAD) {
+            res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else {
+            res = reduce_linfit<S>(g, cur, __reduce_max_sync(0xffffffffu, cur), a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
+        }
+        if (valid) store_result(a, p, cur == 0 ? a.ref_loc : res);   // stack.go:388-397
+        __syncwarp();
+    }
+    if (MODE >= ST_SIGMA) {
+        // clip totals (stack.go:193-198): warp reduce, one atomic pair per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ncl += __shfl_xor_sync(0xffffffffu, ncl, o);
+            nch += __shfl_xor_sync(0xffffffffu, nch, o);
+        }
+        if (lane == 0 && (ncl | nch)) {
+            atomicAdd(a.clip + 0, (unsigned long long)ncl);
+            atomicAdd(a.clip + 1, (unsigned long long)nch);
+        }
+    }
+}
+
+}  // namespace nl
+
+struct nl_stack_job {
+    nl_ctx *ctx = nullptr;
+    int n = 0;
+    long long pixels = 0;
+    float *frames = nullptr;          // [n][pixels]
+    float *out = nullptr;             // [pixels], used by nl_stack_run
+    float *weights = nullptr;         // [n]
+    float *ramp = nullptr;            // [2*(n+1)]
+    bool ramp_ready = false;
+    unsigned long long *clip = nullptr;   // [3] device: clip low, clip high, tile counter
+    unsigned long long *clip_host = nullptr;   // [2] pinned
+    alignas(64) CUtensorMap tmap;     // [n][pixels] fp32, box 32 frames x 32 pixels, NaN fill
+    bool tmap_ok = false;
+};
+
+namespace nl {
+
+template <int MODE, bool W, int S, typename IDX>
+inline int launch_column(nl_stack_job *job, const StackArgs &args) {
+    nl_ctx *ctx = job->ctx;
+    constexpr int SB = SlotBytes<MODE, W, IDX>::value;
+    const size_t gap = (size_t)(QW - 1) * S * sizeof(float);      // in front of, between and behind the warp slabs
+    const size_t per_warp = (size_t)SB * S * ((job->n + 31) & ~31) + gap;
+    const size_t cap = (size_t)ctx->max_smem_optin;
+    if (per_warp + gap > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
+    int warps = (int)((cap - gap) / per_warp);
+    if (warps > 8) warps = 8;
+    const size_t smem = per_warp * warps + gap;                   // (the tile mbarriers live in the tail of the last gap)
+    auto kern = stack_column_kernel<MODE, W, S, IDX>;
+    NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 0;
+    NL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const long long tiles = (job->pixels + S - 1) / S;
+    long long grid = (long long)ctx->sm_count * ctas_per_sm;
+    const long long need = (tiles + warps - 1) / warps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(args, job->tmap);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}
+
+template <int MODE, bool W, typename IDX>
+inline int launch_column_i(nl_stack_job *job, const StackArgs &args) {
+    constexpr int SB = SlotBytes<MODE, W, IDX>::value;
+    const size_t per_pixel = (size_t)SB * ((job->n + 31) & ~31);
+    const size_t gap = (size_t)(QW - 1) * sizeof(float);           // per pixel of tile width
+    const size_t cap = (size_t)job->ctx->max_smem_optin;
+    // Tile width: a wide tile uses every lane of a warp but needs SB*npad*S bytes per warp, and the kernel
+    // lives on latency hiding across warps (each column is a serial dependency chain).  Score = columns
+    // that make progress per cycle ~ min(warps, 8) * S; e.g. N=256 -> 32 pixels x 7 warps, N=1024 ->
+    // 8 pixels x 7 warps instead of 32 pixels x 1 warp.
+    const int widths[4] = {32, 16, 8, 1};
+    int best = 0;
+    double best_score = -1;
+    for (int wdt : widths) {
+        const size_t per_warp = (per_pixel + gap) * wdt;
+        if (per_warp + gap * wdt > cap) continue;
+        size_t warps = (cap - gap * wdt) / per_warp;
+        if (warps > 64) warps = 64;
+        const double score = (double)(warps > 8 ? 8 : warps) * wdt;
+        if (score > best_score) { best_score = score; best = wdt; }
+    }
+    if (const char *force = getenv("NL_TILE_WIDTH")) {             // development override (A/B measurements)
+        const int wdt = atoi(force);
+        if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + 2 * gap) * wdt <= cap) best = wdt;
+    }
+    switch (best) {
+    case 32: return launch_column<MODE, W, 32, IDX>(job, args);
+    case 16: return launch_column<MODE, W, 16, IDX>(job, args);
+    case 8: return launch_column<MODE, W, 8, IDX>(job, args);
+    case 1: return launch_column<MODE, W, 1, IDX>(job, args);
+    }
+    return set_error(NL_E_INVALID, "n_frames %d too large for shared memory", job->n);
+}
+
+template <int MODE, bool W>
+inline int launch_column_s(nl_stack_job *job, const StackArgs &args) {
+    if (!W || job->n <= 256) return launch_column_i<MODE, W, unsigned char>(job, args);
+    if (job->n <= 65536) return launch_column_i<MODE, W, unsigned short>(job, args);
+    return set_error(NL_E_INVALID, "weighted stacking of more than 65536 frames is not supported");
+}
+
+// per-mode launchers, one translation unit each
+int launch_median(nl_stack_job *job, const StackArgs &args);
+int launch_sigma(nl_stack_job *job, const StackArgs &args, bool weighted);
+int launch_winsor(nl_stack_job *job, const StackArgs &args, bool weighted);
+int launch_mad(nl_stack_job *job, const StackArgs &args);
+int launch_linfit(nl_stack_job *job, const StackArgs &args);
+
+}  // namespace nl
