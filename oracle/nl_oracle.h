@@ -108,6 +108,19 @@ float nlo_median_f32(float *a, int n);
 float nlo_gather_and_median(const float *data, int32_t len, int32_t index, const int32_t *mask, int nmask, float *buffer);
 int   nlo_create_mask(int32_t width, float radius, int32_t *mask, int cap);
 
+/* ---- amd64 numerics of the path's neighbours (nl_oracle_amd64.c): stats_amd64.s, noise_amd64.s,
+ *      median3x3_amd64.s restated lane by lane, and the pure-Go definitions beside them ---- */
+void   nlo_calc_min_mean_max_purego(const float *data, int64_t n, float *min, float *mean, float *max);
+double nlo_calc_variance_purego(const float *data, int64_t n, float mean);
+void   nlo_calc_min_mean_max_avx2(const float *data, int64_t n, float *min, float *mean, float *max);   /* n % 4 == 0 */
+double nlo_calc_variance_avx2(const float *data, int64_t n, float mean);                                /* n % 4 == 0 */
+void   nlo_stats(const float *data, int64_t n, int amd64, float out[4]);   /* {min, mean, max, stddev}, stats.go:102-153 */
+float  nlo_estimate_noise_line_avx2(const float *rows3, int64_t width);
+float  nlo_estimate_noise_amd64(const float *data, int32_t width, int32_t height);
+void   nlo_median_filter3x3(float *out, const float *data, int32_t width, int32_t height, int amd64);
+int64_t nlo_bad_pixel_map(const float *data, int64_t len, int32_t width, float sigma_low, float sigma_high, int amd64,
+                          float *tmp, int32_t *bpm, int64_t cap, float stats[4]);
+
 /* ---- internal/star/findstars.go, internal/star/qsort.go ---- */
 int   nlo_find_bright_pixels(const float *data, int32_t len, int32_t width, float threshold, int32_t radius,
                              nlo_star *stars, int cap);

@@ -29,7 +29,7 @@ class Transform(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, "nl_oracle.c"), os.path.join(_HERE, "nl_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("nl_oracle.c", "nl_oracle_amd64.c", "nl_oracle_simd.c", "nl_oracle.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -82,8 +82,81 @@ def lib():
         L.nlo_synth_frame.argtypes = [fp, C.c_uint64, C.c_size_t, C.c_uint32, C.c_uint32]
         L.nlo_lowbias32.restype = C.c_uint32
         L.nlo_lowbias32.argtypes = [C.c_uint32]
+        L.nlo_stats.argtypes = [fp, C.c_int64, C.c_int, fp]
+        L.nlo_estimate_noise_amd64.restype = C.c_float
+        L.nlo_estimate_noise_amd64.argtypes = [fp, C.c_int32, C.c_int32]
+        L.nlo_estimate_noise_line_avx2.restype = C.c_float
+        L.nlo_estimate_noise_line_avx2.argtypes = [fp, C.c_int64]
+        L.nlo_median_filter3x3.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_int]
+        L.nlo_bad_pixel_map.restype = C.c_int64
+        L.nlo_bad_pixel_map.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int, fp,
+                                        C.POINTER(C.c_int32), C.c_int64, fp]
+        L.nlo_calc_variance_avx2.restype = C.c_double
+        L.nlo_calc_variance_avx2.argtypes = [fp, C.c_int64, C.c_float]
+        L.nlo_calc_min_mean_max_avx2.argtypes = [fp, C.c_int64, fp, fp, fp]
         _lib = L
     return _lib
+
+
+_simd = None
+
+
+def simd():
+    """libnl_oracle_simd.so (the AVX2 kernels replayed with real instructions), or None when this host
+    has no AVX2+FMA or the file did not build.  Only a cross-check of nl_oracle_amd64.c."""
+    global _simd
+    if _simd is None:
+        build()
+        so = os.path.join(_HERE, "libnl_oracle_simd.so")
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            flags = ""
+        if not os.path.exists(so) or " avx2" not in flags or " fma" not in flags:
+            _simd = False
+        else:
+            L = C.CDLL(so)
+            fp = C.POINTER(C.c_float)
+            L.nlo_simd_min_mean_max.argtypes = [fp, C.c_int64, fp, fp, fp]
+            L.nlo_simd_variance.restype = C.c_double
+            L.nlo_simd_variance.argtypes = [fp, C.c_int64, C.c_float]
+            L.nlo_simd_noise_line.restype = C.c_float
+            L.nlo_simd_noise_line.argtypes = [fp, C.c_int64]
+            L.nlo_simd_median_line.argtypes = [fp, fp, C.c_int64]
+            _simd = L
+    return _simd or None
+
+
+def stats(data, amd64=True):
+    """Stats.Min/Mean/Max/StdDev -> float32[4]"""
+    data = np.ascontiguousarray(data, dtype=np.float32).ravel()
+    out = np.zeros(4, np.float32)
+    lib().nlo_stats(_fp(data), data.size, int(amd64 and data.size % 4 == 0), _fp(out))
+    return out
+
+
+def estimate_noise(data, width, amd64=True):
+    data = np.ascontiguousarray(data, dtype=np.float32).ravel()
+    f = lib().nlo_estimate_noise_amd64 if amd64 else lib().nlo_estimate_noise
+    return np.float32(f(_fp(data), int(width), data.size // int(width)))
+
+
+def median_filter3x3(data, width, amd64=True):
+    data = np.ascontiguousarray(data, dtype=np.float32).ravel()
+    out = np.empty_like(data)
+    lib().nlo_median_filter3x3(_fp(out), _fp(data), int(width), data.size // int(width), int(amd64))
+    return out
+
+
+def bad_pixel_map(data, width, sigma_low, sigma_high, amd64=True):
+    """pre.BadPixelMap -> (bpm int32[], stats float32[4] of data - median3x3, diff image)"""
+    data = np.ascontiguousarray(data, dtype=np.float32).ravel()
+    tmp = np.empty_like(data)
+    bpm = np.empty(data.size, np.int32)
+    st = np.zeros(4, np.float32)
+    n = lib().nlo_bad_pixel_map(_fp(data), data.size, int(width), float(sigma_low), float(sigma_high), int(amd64),
+                                _fp(tmp), bpm.ctypes.data_as(C.POINTER(C.c_int32)), bpm.size, _fp(st))
+    return bpm[:n].copy(), st, tmp
 
 
 def _fp(a):
