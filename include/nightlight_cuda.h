@@ -110,13 +110,46 @@ int  nl_auto_select_mode(int32_t n_frames);
 int  nl_get_weights(int32_t weighting, const float *exposure, const float *noise, const float *hfr,
                     int32_t n_frames, float *weights);
 
-/* ---- noise estimate: replaces stats.EstimateNoise, portable definition (internal/stats/noise.go:24-55),
+/* ---- numerics of the frame statistics ------------------------------------------------------
+ * The reference computes EstimateNoise, Stats.Min/Mean/Max/StdDev and MedianFilter3x3 with AVX2 assembly on
+ * amd64 CPUs that have AVX2 (cpuid dispatch: noise_amd64.go:25-30, stats_amd64.go:24-45, median3x3_amd64.go:26-32)
+ * and with pure-Go loops everywhere else; the two round differently (lane order, fused multiply-adds, min/max
+ * operand roles).  A context reproduces one of them bit for bit; the default is the amd64 one.  Images too
+ * narrow or arrays too ragged for the SIMD kernels (width < 8, length % 4 != 0: the assembly reads outside
+ * its slice there) take the pure-Go definition in either setting. */
+enum { NL_NUMERICS_AMD64 = 0, NL_NUMERICS_PUREGO = 1 };
+int  nl_ctx_set_numerics(nl_ctx *ctx, int32_t numerics);
+/* how many float64 summation chains had to be replayed in order because the interval around the parallel sum
+ * straddled a float32 rounding boundary (diagnostics; see nl_prestats.cu) */
+int  nl_ctx_exact_replays(nl_ctx *ctx, int64_t *replays);
+
+/* ---- noise estimate: replaces stats.EstimateNoise (internal/stats/noise_amd64.go:25-43 + noise_amd64.s:75-192,
+ * or noise.go:24-55 in pure-Go numerics),
  * the per-frame scalar behind StWeightInverseNoise (stack.go:247-259).  n_frames frames of width x height
  * pixels, frame i at dev_frames + i*frame_stride (e.g. the buffer of a stack job holding whole frames);
  * one launch for all frames, results to host memory. */
 int  nl_estimate_noise_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t width,
                            int32_t height, float *host_noise);
 int  nl_estimate_noise(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float *noise);
+
+/* ---- frame statistics and bad-pixel map -----------------------------------
+ * nl_median_filter3x3: median.MedianFilter3x3 (internal/median/median3x3_amd64.go:24-48, median3x3.go:26-110):
+ *   interior pixels = median of their 3x3 neighbourhood, border rows and columns copied.
+ * nl_stats: stats = {Min, Mean, Max, StdDev} of Stats (internal/stats/stats.go:102-153; calcMinMeanMax and
+ *   calcVariance, stats_amd64.s:27-143 / stats.go:264-287): float64 sums in the reference's lane order,
+ *   mean = float32(sum/len), stddev = float32(sqrt(sum of squared fp32 deviations / len)).
+ * nl_bad_pixel_map: pre.BadPixelMap (internal/ops/pre/badpixels.go:32-51): tmp = data - median3x3(data),
+ *   stats of tmp (the reference's medianDiffStats; stats[3] is the medianDiffStats.StdDev() that star
+ *   detection takes, findstars.go:134-169), indices with tmp < -stddev*sigma_low or tmp > stddev*sigma_high
+ *   in ascending order.  *count = number found; the first min(count, cap) are written to bpm. */
+int  nl_median_filter3x3(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float *host_out);
+int  nl_median_filter3x3_dev(nl_ctx *ctx, const float *dev_data, int32_t width, int32_t height, float *dev_out);
+int  nl_stats(nl_ctx *ctx, const float *host_data, int64_t len, float stats[4]);
+int  nl_stats_dev(nl_ctx *ctx, const float *dev_data, int64_t len, float stats[4]);
+int  nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
+                      int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]);
+int  nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
+                          float *dev_tmp, int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]);
 
 /* ---- batches: replaces StackIncremental / StackIncrementalFinalize (stack.go:924-944) -------
  * acc = light*weight (first != 0) or acc += light*weight; then acc *= 1/weight_sum.  Device buffers. */

@@ -11,9 +11,10 @@ call needs the built library and a CUDA device and raises otherwise.
 from .binding import (  # noqa: F401
     NightlightError, load_library, library_path, Context, StackJob, Star, STAR_DTYPE,
     ST_MEDIAN, ST_MEAN, ST_SIGMA, ST_WINSOR_SIGMA, ST_MAD_SIGMA, ST_LINEAR_FIT, ST_AUTO,
-    W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR, DECLARED_SYMBOLS,
+    W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR, DECLARED_SYMBOLS, NUMERICS_AMD64, NUMERICS_PUREGO,
 )
 from .ops import (OpStack, OpStackBatches, project, transform_invert, find_bright_pixels, find_stars, get_weights,  # noqa: F401
-                  find_sigmas_and_stack, estimate_noise, project_scaled, fits_decode, fits_encode, partition)
+                  find_sigmas_and_stack, estimate_noise, project_scaled, fits_decode, fits_encode, partition,
+                  median_filter3x3, stats, bad_pixel_map)
 
 __version__ = "0.1.0"

@@ -10,6 +10,7 @@ _SO = os.environ.get("NL_CUDA_LIB") or os.path.join(_HERE, "libnightlight_cuda.s
 
 ST_MEDIAN, ST_MEAN, ST_SIGMA, ST_WINSOR_SIGMA, ST_MAD_SIGMA, ST_LINEAR_FIT, ST_AUTO = range(7)
 W_NONE, W_EXPOSURE, W_INVERSE_NOISE, W_INVERSE_HFR = range(4)
+NUMERICS_AMD64, NUMERICS_PUREGO = 0, 1
 
 NL_E_INVALID, NL_E_CUDA, NL_E_UNSUPPORTED, NL_E_SINGULAR, NL_E_NOMEM, NL_E_WEIGHTS = -1, -2, -3, -4, -5, -6
 
@@ -60,6 +61,14 @@ DECLARED_SYMBOLS = {
     "nl_get_weights": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, _fp]),
     "nl_estimate_noise_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _fp]),
     "nl_estimate_noise": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _fp]),
+    "nl_ctx_set_numerics": (C.c_int, [_vp, C.c_int32]),
+    "nl_ctx_exact_replays": (C.c_int, [_vp, _i64p]),
+    "nl_median_filter3x3": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "nl_median_filter3x3_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "nl_stats": (C.c_int, [_vp, _vp, C.c_int64, _fp]),
+    "nl_stats_dev": (C.c_int, [_vp, _vp, C.c_int64, _fp]),
+    "nl_bad_pixel_map": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, _i32p, C.c_int64, _i64p, _fp]),
+    "nl_bad_pixel_map_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, _vp, _i32p, C.c_int64, _i64p, _fp]),
     "nl_stack_incremental_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_int]),
     "nl_stack_incremental_finalize_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_float]),
     "nl_transform_invert": (C.c_int, [_fp, _fp]),
@@ -161,6 +170,15 @@ class Context:
         s = _vp()
         check(load_library().nl_ctx_stream(self._h, C.byref(s)))
         return s.value or 0
+
+    def set_numerics(self, numerics):
+        """NUMERICS_AMD64 (default: the reference's AVX2 kernels) or NUMERICS_PUREGO for the frame statistics"""
+        check(load_library().nl_ctx_set_numerics(self._h, int(numerics)))
+
+    def exact_replays(self):
+        n = C.c_int64()
+        check(load_library().nl_ctx_exact_replays(self._h, C.byref(n)))
+        return n.value
 
     def mem_info(self):
         """(free, total) bytes of device memory"""

@@ -18,6 +18,8 @@ struct nl_ctx {
     int max_smem_optin = 0;          // bytes of dynamic shared memory one CTA may opt in to
     int smem_per_sm = 0;
     std::atomic<int64_t> launches{0};
+    int numerics = NL_NUMERICS_AMD64;   // which build of the reference the frame statistics reproduce (nl_ctx_set_numerics)
+    int64_t exact_replays = 0;          // float64 chains that had to be replayed in order (nl_prestats.cu)
     // scratch owned by the context, grown on demand (star scan)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -37,6 +39,7 @@ namespace nl {
 int set_error(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int ensure_scratch(nl_ctx *ctx, size_t bytes);
+int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total);   // nl_stars.cu
 int fits_decode_launch(nl_ctx *ctx, const void *dev_raw, int bitpix, long long n, float bscale, float bzero, float *dev_dst);
 
 #define NL_CUDA(call)                                        \

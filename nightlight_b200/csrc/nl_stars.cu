@@ -117,6 +117,13 @@ __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict
     if (threadIdx.x == 0) *total = carry;
 }
 
+int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total) {
+    row_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(dev_counts, dev_offsets, n, dev_total);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
+}
+
 // pass 1: per-row counts and offsets; *count = number of candidates in the frame
 static int bright_count(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius, int *count) {
     *count = 0;

@@ -157,8 +157,42 @@ class OpStackBatches:
         return Image(data=out, naxisn=tuple(batches[0][0].naxisn), exposure=float(exposure))
 
 
+def median_filter3x3(ctx: B.Context, data, width):
+    """median.MedianFilter3x3 (median3x3_amd64.go:24-48 / median3x3.go:26-38) -> float32[len]"""
+    data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+    out = np.empty_like(data)
+    check(load_library().nl_median_filter3x3(ctx.handle, data.ctypes.data_as(C.c_void_p), data.size, int(width),
+                                             out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def stats(ctx: B.Context, data):
+    """Stats.Min/Mean/Max/StdDev (stats.go:102-153) -> float32[4] = min, mean, max, stddev"""
+    data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+    out = np.zeros(4, dtype=np.float32)
+    check(load_library().nl_stats(ctx.handle, data.ctypes.data_as(C.c_void_p), data.size, out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+
+def bad_pixel_map(ctx: B.Context, data, width, sigma_low, sigma_high, cap=None):
+    """pre.BadPixelMap (badpixels.go:32-51) -> (bpm int32[], medianDiffStats float32[4] = min, mean, max, stddev)"""
+    data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+    cap = data.size // 100 + 1024 if cap is None else int(cap)
+    st = np.zeros(4, dtype=np.float32)
+    lib = load_library()
+    while True:
+        bpm = np.empty(cap, dtype=np.int32)
+        n = C.c_int64()
+        check(lib.nl_bad_pixel_map(ctx.handle, data.ctypes.data_as(C.c_void_p), data.size, int(width), float(sigma_low),
+                                   float(sigma_high), bpm.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(n),
+                                   st.ctypes.data_as(C.POINTER(C.c_float))))
+        if n.value <= cap:
+            return bpm[:n.value].copy(), st
+        cap = n.value
+
+
 def estimate_noise(ctx: B.Context, data, width):
-    """stats.EstimateNoise (portable definition, noise.go:24-55) of one frame -> float32"""
+    """stats.EstimateNoise (noise_amd64.go:25-43, or noise.go:24-55 in pure-Go numerics) of one frame -> float32"""
     data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
     out = C.c_float()
     check(load_library().nl_estimate_noise(ctx.handle, data.ctypes.data_as(C.c_void_p), data.size, int(width), C.byref(out)))

@@ -1,0 +1,128 @@
+"""SURVEY.md 8f N3 on the device: MedianFilter3x3, Stats.Min/Mean/Max/StdDev and pre.BadPixelMap, bit-exact
+against the oracle in both numerics of the reference (AVX2 assembly of amd64 builds / pure-Go loops)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import nightlight_b200 as nl  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    with nl.Context(0) as c:
+        yield c
+
+
+@pytest.fixture(params=[True, False], ids=["amd64", "purego"])
+def numerics(request, ctx):
+    ctx.set_numerics(nl.NUMERICS_AMD64 if request.param else nl.NUMERICS_PUREGO)
+    yield request.param
+    ctx.set_numerics(nl.NUMERICS_AMD64)
+
+
+def frame(w, h, seed, specials=False, scale=37.0, offset=900.0):
+    rng = np.random.default_rng(seed)
+    img = (rng.standard_normal((h, w)) * scale + offset).astype(np.float32)
+    img[rng.random((h, w)) < 0.002] += np.float32(5000)
+    if specials:
+        m = rng.random((h, w))
+        img[m < 0.02] = np.float32(0.0)
+        img[(m >= 0.02) & (m < 0.04)] = np.float32(-0.0)
+        img[(m >= 0.04) & (m < 0.05)] = np.nan
+        img[(m >= 0.05) & (m < 0.055)] = np.inf
+    return img
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return np.array_equal(a.view(np.uint32)[~(np.isnan(a) & np.isnan(b))], b.view(np.uint32)[~(np.isnan(a) & np.isnan(b))])
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 5), (3, 3), (7, 4), (8, 3), (9, 9), (61, 23), (64, 64), (257, 130), (1500, 700)])
+@pytest.mark.parametrize("specials", [False, True])
+def test_median_filter3x3(ctx, numerics, w, h, specials):
+    img = frame(w, h, w * 31 + h, specials)
+    got = nl.median_filter3x3(ctx, img, w)
+    want = O.median_filter3x3(img, w, amd64=numerics)
+    assert same_bits(got, want), np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0][:8]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 127, 128, 4095, 4096, 4097, 5000, 1 << 16, (1 << 20) + 4, 3000 * 2000])
+def test_stats_min_mean_max_stddev(ctx, numerics, n):
+    data = frame(n, 1, n % 1000 + 5).ravel()
+    got = nl.stats(ctx, data)
+    want = O.stats(data, amd64=numerics)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, got, want)
+
+
+def test_stats_signed_zero_and_nan_extremes(ctx, numerics):
+    """min/max follow the operand roles of VMINPS/VMAXPS (amd64) or the Go comparisons: the sign of a zero
+    extreme and what a NaN does to the running extreme are part of the result"""
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.integers(1, 300)) * 4
+        data = np.abs(rng.standard_normal(n)).astype(np.float32) * (1 if trial % 2 else -1)
+        k = rng.integers(0, n, size=int(rng.integers(1, 12)))
+        data[k] = np.where(rng.random(k.size) < 0.5, np.float32(0.0), np.float32(-0.0))
+        if trial % 3 == 0:
+            data[rng.integers(0, n, size=3)] = np.nan
+        got, want = nl.stats(ctx, data), O.stats(data, amd64=numerics)
+        assert same_bits(got[[0, 2]], want[[0, 2]]), (trial, got, want)
+        assert np.isnan(got[[0, 2]]).tolist() == np.isnan(want[[0, 2]]).tolist()
+
+
+def test_stats_near_rounding_boundaries_take_the_exact_replay(ctx):
+    """Data built so that the float64 sum sits on a float32 rounding boundary of the mean: the interval test
+    cannot decide, the chains are replayed in order, and the result still equals the oracle's bit for bit"""
+    ctx.set_numerics(nl.NUMERICS_AMD64)
+    before = ctx.exact_replays()
+    n = 1 << 16
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        data = (rng.standard_normal(n) * 3 + 50).astype(np.float32)
+        # steer the sum onto the midpoint between two neighbouring float32 means
+        s = float(np.sum(data.astype(np.float64)))
+        m = np.float32(s / n)
+        mid = (float(m) + float(np.nextafter(m, np.float32(np.inf)))) / 2
+        data[0] = np.float32(float(data[0]) + (mid * n - s))
+        got, want = nl.stats(ctx, data), O.stats(data, amd64=True)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (seed, got, want)
+    assert ctx.exact_replays() > before
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (333, 257), (1500, 1000)])
+def test_bad_pixel_map(ctx, numerics, w, h):
+    img = frame(w, h, 9 + w)
+    bpm, st = nl.bad_pixel_map(ctx, img, w, 3.0, 5.0)
+    want_bpm, want_st, _ = O.bad_pixel_map(img, w, 3.0, 5.0, amd64=numerics)
+    assert np.array_equal(st.view(np.uint32), want_st.view(np.uint32)), (st, want_st)
+    assert np.array_equal(bpm, want_bpm) and len(bpm) > 0
+
+
+def test_bad_pixel_map_truncated_list_still_counts(ctx):
+    w, h = 200, 100
+    img = frame(w, h, 77)
+    full, _ = nl.bad_pixel_map(ctx, img, w, 1.0, 1.0)
+    part, _ = nl.bad_pixel_map(ctx, img, w, 1.0, 1.0, cap=5)       # the wrapper retries with the reported count
+    assert np.array_equal(full, part) and len(full) > 5
+
+
+def test_star_detection_threshold_from_device_stats(ctx):
+    """medianDiffStats.StdDev() of BadPixelMap is what FindStars takes as its bad-pixel scale (findstars.go:134-169):
+    the whole detection input now comes from the device"""
+    from test_gpu_project_stars import star_field
+    w, h = 400, 300
+    img = star_field(w, h, 25, seed=8)
+    _, st = nl.bad_pixel_map(ctx, img, w, 3.0, 5.0)
+    _, want_st, _ = O.bad_pixel_map(img, w, 3.0, 5.0, amd64=True)
+    assert st[3].view(np.uint32) == want_st[3].view(np.uint32)
+    loc, scale = np.float32(np.median(img)), np.float32(3.0)
+    stars, shifts, hfr = nl.find_stars(ctx, img, w, loc, scale, 10.0, 5.0, 1.4, 12, float(st[3]))
+    want = O.find_stars(img, w, loc, scale, 10.0, 5.0, 1.4, 12, float(want_st[3]))
+    assert len(stars) == len(want[0]) and len(stars) > 5

@@ -127,15 +127,19 @@ def test_config3_pipeline_detect_project_stack(ctx):
         assert got[1:] == want[1:]
 
 
-@pytest.mark.parametrize("w,h", [(64, 48), (333, 257), (3, 3), (5, 4), (1024, 1024)])
-def test_estimate_noise_matches_oracle(ctx, w, h):
-    """stats.EstimateNoise (portable definition) on the device: bit-exact against the oracle"""
-    import ctypes as C
+@pytest.mark.parametrize("amd64", [True, False])
+@pytest.mark.parametrize("w,h", [(64, 48), (333, 257), (3, 3), (5, 4), (7, 9), (8, 3), (9, 5), (13, 6), (14, 14), (1024, 1024), (1021, 37)])
+def test_estimate_noise_matches_oracle(ctx, w, h, amd64):
+    """stats.EstimateNoise on the device, bit-exact against the oracle in both of the reference's
+    summation orders: the AVX2 lanes with fused multiply-adds (amd64 builds) and the pure-Go loop"""
     rng = np.random.default_rng(w + h)
     img = (rng.standard_normal(w * h) * 11 + 500).astype(np.float32)
-    O.lib().nlo_estimate_noise.restype = C.c_float
-    want = np.float32(O.lib().nlo_estimate_noise(img.ctypes.data_as(C.POINTER(C.c_float)), w, h))
-    got = nl.estimate_noise(ctx, img, w)
+    want = O.estimate_noise(img, w, amd64=amd64)
+    ctx.set_numerics(nl.NUMERICS_AMD64 if amd64 else nl.NUMERICS_PUREGO)
+    try:
+        got = nl.estimate_noise(ctx, img, w)
+    finally:
+        ctx.set_numerics(nl.NUMERICS_AMD64)
     assert got.view(np.uint32) == want.view(np.uint32) or (np.isnan(got) and np.isnan(want)), (got, want)
 
 
@@ -147,8 +151,7 @@ def test_inverse_noise_weights_from_resident_frames(ctx):
     w, h, n = 96, 64, 18
     rng = np.random.default_rng(2)
     frames = [(rng.standard_normal(w * h) * (5 + k % 4) + 300).astype(np.float32) for k in range(n)]
-    O.lib().nlo_estimate_noise.restype = C.c_float
-    noise = np.array([O.lib().nlo_estimate_noise(f.ctypes.data_as(C.POINTER(C.c_float)), w, h) for f in frames], np.float32)
+    noise = np.array([O.estimate_noise(f, w, amd64=True) for f in frames], np.float32)
     with nl.StackJob(ctx, n, w * h) as job:
         for i, f in enumerate(frames):
             job.put_frame(i, f)
