@@ -265,6 +265,45 @@ float EstimateNoise(Context &c, const std::vector<float> &data, int32_t width) {
     return noise;
 }
 
+BasicStats NewStats(Context &c, const std::vector<float> &data) {
+    float st[4] = {0, 0, 0, 0};
+    check(nl_stats(c.Device(0), data.data(), (int64_t)data.size(), st));
+    return BasicStats{st[0], st[1], st[2], st[3]};
+}
+
+std::vector<float> MedianFilter3x3(Context &c, const std::vector<float> &data, int32_t width) {
+    std::vector<float> out(data.size());
+    check(nl_median_filter3x3(c.Device(0), data.data(), (int32_t)data.size(), width, out.data()));
+    return out;
+}
+
+std::vector<int32_t> BadPixelMap(Context &c, const std::vector<float> &data, int32_t width, float sigmaLow, float sigmaHigh,
+                                 BasicStats *medianDiffStats) {
+    std::vector<int32_t> bpm(data.size() / 100 + 1024);       // badpixels.go:42
+    int64_t count = 0;
+    float st[4] = {0, 0, 0, 0};
+    check(nl_bad_pixel_map(c.Device(0), data.data(), (int64_t)data.size(), width, sigmaLow, sigmaHigh, bpm.data(), (int64_t)bpm.size(),
+                           &count, st));
+    if (count > (int64_t)bpm.size()) {
+        bpm.resize((size_t)count);
+        check(nl_bad_pixel_map(c.Device(0), data.data(), (int64_t)data.size(), width, sigmaLow, sigmaHigh, bpm.data(),
+                               (int64_t)bpm.size(), &count, st));
+    }
+    bpm.resize((size_t)count);
+    if (medianDiffStats) *medianDiffStats = BasicStats{st[0], st[1], st[2], st[3]};
+    return bpm;
+}
+
+void OpBadPixel::Apply(Image &f, Context &c, BasicStats *medianDiffStats) {
+    if (SigmaLow == 0 || SigmaHigh == 0) return;              // preprocess.go:181-183
+    int64_t removed = 0;
+    float st[4] = {0, 0, 0, 0};
+    check(nl_op_bad_pixel(c.Device(0), f.Data.data(), (int64_t)f.Data.size(), f.Naxisn[0], SigmaLow, SigmaHigh, &removed, st));
+    if (medianDiffStats) *medianDiffStats = BasicStats{st[0], st[1], st[2], st[3]};
+    fprintf(c.Log, "%d: Removed %d bad pixels (%.2f%%) with sigma low=%.2f high=%.2f\n", f.ID, (int)removed,
+            (double)(100.0f * (float)removed / (float)f.Pixels), (double)SigmaLow, (double)SigmaHigh);     // :190-191
+}
+
 // ------------------------------------------------------------------------------------------------
 // Stacking
 // ------------------------------------------------------------------------------------------------

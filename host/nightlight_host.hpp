@@ -105,7 +105,27 @@ std::vector<Star> FindStars(Context &c, const std::vector<float> &data, int32_t 
                             float starSig, float bpSigma, float starInOut, int32_t radius, float medianDiffStdDev,
                             float *sumOfShifts, float *avgHFR);
 
-// stats.EstimateNoise, portable definition (noise.go:32-55), computed on the device
+// stats.EstimateNoise (noise_amd64.go:25-43; noise.go:32-55 in pure-Go numerics), computed on the device
 float EstimateNoise(Context &c, const std::vector<float> &data, int32_t width);
+
+// The eagerly evaluated part of stats.Stats (stats.go:43-60, 102-153)
+struct BasicStats {
+    float Min = 0, Mean = 0, Max = 0, StdDev = 0;
+};
+BasicStats NewStats(Context &c, const std::vector<float> &data);
+
+// median.MedianFilter3x3, median3x3_amd64.go:24-48
+std::vector<float> MedianFilter3x3(Context &c, const std::vector<float> &data, int32_t width);
+
+// pre.BadPixelMap, badpixels.go:32-51
+std::vector<int32_t> BadPixelMap(Context &c, const std::vector<float> &data, int32_t width, float sigmaLow, float sigmaHigh,
+                                 BasicStats *medianDiffStats);
+
+// pre.OpBadPixel for monochrome frames, preprocess.go:160-201: repairs f.Data in place, sets *medianDiffStats
+// (f.MedianDiffStats) and logs the reference's line.  A zero sigma returns without touching the frame.
+struct OpBadPixel {
+    float SigmaLow = 3, SigmaHigh = 5;
+    void Apply(Image &f, Context &c, BasicStats *medianDiffStats);
+};
 
 }  // namespace nightlight

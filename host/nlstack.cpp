@@ -3,7 +3,7 @@
 // reference's log lines.  Calibration, reference selection and triangle alignment stay with the Go CLI.
 //
 //   nlstack stack [-stMode m] [-stWeight w] [-stSigLow x] [-stSigHigh y] [-stBatch n] [-gpus list] [-out file] in.fits...
-//   nlstack stars [-starSig s] [-starBpSig b] [-starInOut r] [-starRadius r] [-loc l] [-scale s] in.fits...
+//   nlstack stars [-bpSigLow l -bpSigHigh h] [-starSig s] [-starBpSig b] [-starInOut r] [-starRadius r] [-loc l] [-scale s] in.fits...
 //   nlstack project -trans A,B,C,D,E,F [-oob nan|0] -out out.fits in.fits
 #include <chrono>
 #include <cmath>
@@ -35,7 +35,7 @@ int main(int argc, char **argv) {
     const std::string cmd = argv[1];
     std::map<std::string, std::string> flag = {
         {"stMode", "6"}, {"stWeight", "0"}, {"stSigLow", "2.75"}, {"stSigHigh", "2.75"}, {"stBatch", "0"}, {"gpus", "0"},
-        {"out", "out.fits"}, {"starSig", "15"}, {"starBpSig", "0"}, {"starInOut", "1.4"}, {"starRadius", "16"},
+        {"out", "out.fits"}, {"starSig", "15"}, {"starBpSig", "0"}, {"bpSigLow", "0"}, {"bpSigHigh", "0"}, {"starInOut", "1.4"}, {"starRadius", "16"},
         {"loc", "nan"}, {"scale", "nan"}, {"trans", "1,0,0,0,1,0"}, {"oob", "nan"}};
     std::vector<std::string> files;
     for (int i = 2; i < argc; i++) {
@@ -85,10 +85,16 @@ int main(int argc, char **argv) {
                 float loc = (float)atof(flag["loc"].c_str()), scale = (float)atof(flag["scale"].c_str());
                 if (std::isnan(loc)) loc = im->Mean;            // the reference's estimators are randomised: inputs here
                 if (std::isnan(scale)) scale = EstimateNoise(c, im->Data, im->Naxisn[0]);
+                // preprocess.go:88-96: bad-pixel repair runs before star detection and leaves the frame's MedianDiffStats
+                OpBadPixel bp;
+                bp.SigmaLow = (float)atof(flag["bpSigLow"].c_str());
+                bp.SigmaHigh = (float)atof(flag["bpSigHigh"].c_str());
+                BasicStats mds;
+                bp.Apply(*im, c, &mds);
                 float sos = 0, hfr = 0;
                 im->Stars = FindStars(c, im->Data, im->Naxisn[0], loc, scale, (float)atof(flag["starSig"].c_str()),
                                       (float)atof(flag["starBpSig"].c_str()), (float)atof(flag["starInOut"].c_str()),
-                                      atoi(flag["starRadius"].c_str()), 0.0f, &sos, &hfr);
+                                      atoi(flag["starRadius"].c_str()), mds.StdDev, &sos, &hfr);
                 im->HFR = hfr;
                 fprintf(stdout, "%d: Stars %d HFR %.2f\n", im->ID, (int)im->Stars.size(), (double)hfr);   // preprocess.go:455
             }

@@ -150,6 +150,12 @@ int  nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t 
                       int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]);
 int  nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
                           float *dev_tmp, int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]);
+/* OpBadPixel.Apply for monochrome frames (internal/ops/pre/preprocess.go:180-191): BadPixelMap, then
+ * MedianFilterSparse (badpixels.go:79-85) repairs the listed pixels of host_data in place, one after the other.
+ * Returns immediately when either sigma is 0, like the reference.  *removed = number of repaired pixels;
+ * stats = the frame's MedianDiffStats (min, mean, max, stddev). */
+int  nl_op_bad_pixel(nl_ctx *ctx, float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
+                     int64_t *removed, float stats[4]);
 
 /* ---- batches: replaces StackIncremental / StackIncrementalFinalize (stack.go:924-944) -------
  * acc = light*weight (first != 0) or acc += light*weight; then acc *= 1/weight_sum.  Device buffers. */

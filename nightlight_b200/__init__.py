@@ -15,6 +15,6 @@ from .binding import (  # noqa: F401
 )
 from .ops import (OpStack, OpStackBatches, project, transform_invert, find_bright_pixels, find_stars, get_weights,  # noqa: F401
                   find_sigmas_and_stack, estimate_noise, project_scaled, fits_decode, fits_encode, partition,
-                  median_filter3x3, stats, bad_pixel_map)
+                  median_filter3x3, stats, bad_pixel_map, op_bad_pixel)
 
 __version__ = "0.1.0"

@@ -27,6 +27,8 @@
 #include <float.h>
 #include <math.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 
 namespace nl {
 
@@ -63,6 +65,25 @@ template <bool AMD64> __device__ __forceinline__ float median9(float a0, float a
     return a4;
 }
 
+// The same network on the hardware min/max.  FMNMX differs from both numerics only when a NaN or zeros of both signs
+// take part (equal non-zero values are the same bits whichever operand wins), so windows without NaN or zero use it.
+__device__ __forceinline__ float median9_fast(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+                                              float a8) {
+#define NL_SW(i, j) { const float lo_ = fminf(i, j); j = fmaxf(i, j); i = lo_; }
+    NL_SW(a0, a1) NL_SW(a3, a4) NL_SW(a6, a7) NL_SW(a1, a2) NL_SW(a4, a5) NL_SW(a7, a8) NL_SW(a0, a1) NL_SW(a3, a4) NL_SW(a6, a7)
+    a3 = fmaxf(a0, a3); a6 = fmaxf(a3, a6);
+    NL_SW(a1, a4)
+    a4 = fminf(a4, a7); a4 = fmaxf(a1, a4);
+    a5 = fminf(a5, a8); a2 = fminf(a2, a5);
+    NL_SW(a2, a4)
+    a4 = fminf(a4, a6); a4 = fmaxf(a2, a4);
+#undef NL_SW
+    return a4;
+}
+
+// NaN or a zero of either sign: (bits << 1) is 0 for zeros and above 0xff000000 for NaN
+__device__ __forceinline__ bool nan_or_zero(float v) { const uint32_t b = __float_as_uint(v) << 1; return b == 0u || b > 0xff000000u; }
+
 // One column x four rows per thread with the three-column window of six rows in registers; lanes
 // cover consecutive columns, so loads and stores are full 128-byte lines and the neighbouring
 // columns come from L1.  DIFF: writes data - median (badpixels.go:34-35) instead of the median.
@@ -73,20 +94,26 @@ __global__ void __launch_bounds__(256) median3x3_kernel(const float *__restrict_
     if (x >= w || y0 >= h) return;
     const int xl = x > 0 ? x - 1 : x, xr = x < w - 1 ? x + 1 : x;
     float l[6], c[6], r[6];
+    bool special[6];                                              // a NaN or a zero in this row of the window
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         int y = y0 - 1 + k;
         y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
         const float *row = data + (size_t)y * w;
         l[k] = __ldg(row + xl); c[k] = __ldg(row + x); r[k] = __ldg(row + xr);
+        special[k] = nan_or_zero(l[k]) | nan_or_zero(c[k]) | nan_or_zero(r[k]);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int y = y0 + k;
         if (y >= h) break;
         float m = c[k + 1];                                       // border rows and columns are copied
-        if (x > 0 && x < w - 1 && y > 0 && y < h - 1)
-            m = median9<AMD64>(l[k], c[k], r[k], l[k + 1], c[k + 1], r[k + 1], l[k + 2], c[k + 2], r[k + 2]);
+        if (x > 0 && x < w - 1 && y > 0 && y < h - 1) {
+            if (special[k] | special[k + 1] | special[k + 2])
+                m = median9<AMD64>(l[k], c[k], r[k], l[k + 1], c[k + 1], r[k + 1], l[k + 2], c[k + 2], r[k + 2]);
+            else
+                m = median9_fast(l[k], c[k], r[k], l[k + 1], c[k + 1], r[k + 1], l[k + 2], c[k + 2], r[k + 2]);
+        }
         out[(size_t)y * w + x] = DIFF ? __fsub_rn(c[k + 1], m) : m;
     }
 }
@@ -121,12 +148,27 @@ template <bool AMD64, bool MAX> __device__ __forceinline__ Ext ext_join(Ext a, E
     return a;
 }
 
-struct StatRec {            // one record = what one warp saw: 1024 vectors of four consecutive elements
-    double sum[4], mag[4];  // per lane: sum of the terms, sum of their magnitudes
+// A node of the ordered fold: what a contiguous run of chain elements contributes, per lane.
+//   S   parallel sum of the run's terms
+//   A   upper bound on the sum over the run's elements of |partial sum up to that element|, partial sums counted
+//       from the start of the run: a leaf of at most 1024 elements has A = len * (sum of magnitudes)
+//   len chain elements in the run
+// join(a, b) for a before b: S = a.S + b.S, A = a.A + b.A + b.len * |a.S|, len = a.len + b.len.  At the root, u * A
+// bounds the distance of the sequentially rounded chain from the exact sum (u = 2^-53 per addition).
+struct Node {
+    double S[4], A[4];
     Ext mn[4], mx[4];
+    double len;
 };
 
-constexpr int REC_VECS = 1024;      // float4 vectors per record (32 per thread)
+struct StatOut {            // what the host reads back after both passes
+    float mn, mean, mx, stddev;
+    int mean_decided, std_decided;
+    double total[2], bound[2];
+};
+
+constexpr int REC_VECS = 1024;      // float4 vectors per warp (32 per thread)
+constexpr int FOLD_WORKERS = 64;
 
 // term of the chain: the element itself (MODE 0, calcMinMeanMax) or its squared distance from the
 // rounded mean, subtracted in fp32 and squared in float64 (MODE 1, calcVariance)
@@ -136,39 +178,52 @@ template <int MODE> __device__ __forceinline__ double stat_term(float x, float m
     return __dmul_rn(d, d);
 }
 
-// AMD64: lane j of the vectors is its own chain (LANES = 4).  Pure Go: one chain over all elements;
-// a thread's 32 vectors are 128 consecutive elements, kept in slot 0.
+template <bool AMD64> __device__ __forceinline__ Ext ext_empty() { return Ext{AMD64 ? 0.0f : NAN, 2}; }
+
+__device__ __forceinline__ uint32_t dev_f32_bits(float f) { return __float_as_uint(f); }
+
+// One pass over the array (MODE 0: sums and extremes; MODE 1: squared deviations from out->mean).
+// AMD64: lane j of the vectors is its own chain.  Pure Go: one chain over all elements (slot 0); a thread's 32
+// vectors are 128 consecutive elements.  Every CTA folds its eight warps into one node; the CTA that finishes last
+// folds all nodes in order, appends the up-to-three tail elements of a ragged pure-Go array, and decides the
+// float32 result from the interval [total - bound, total + bound] (see the file header).
 template <bool AMD64, int MODE>
-__global__ void __launch_bounds__(256) stats_records_kernel(const float4 *__restrict__ data, long long n_vecs, float mean,
-                                                            StatRec *__restrict__ recs) {
-    const int lane = threadIdx.x & 31;
-    const long long rec = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long v0 = rec * REC_VECS + lane * 32;
-    if (rec * REC_VECS >= n_vecs) return;
+__global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restrict__ data, long long n_vecs, long long n,
+                                                         Node *__restrict__ nodes, unsigned *__restrict__ counter,
+                                                         StatOut *__restrict__ out) {
     constexpr int L = AMD64 ? 4 : 1;
+    __shared__ double sh_S[4][FOLD_WORKERS], sh_A[4][FOLD_WORKERS], sh_len[FOLD_WORKERS];
+    __shared__ Ext sh_mn[4][FOLD_WORKERS], sh_mx[4][FOLD_WORKERS];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float mean = MODE == 1 ? out->mean : 0.0f;
+    const long long rec = (long long)blockIdx.x * 8 + warp;
+    const long long v0 = rec * REC_VECS + lane * 32;
     double sum[L], mag[L];
     Ext mn[L], mx[L];
 #pragma unroll
-    for (int j = 0; j < L; j++) { sum[j] = 0.0; mag[j] = 0.0; mn[j] = Ext{AMD64 ? 0.0f : NAN, 2}; mx[j] = mn[j]; }
-    for (int i0 = 0; i0 < 32; i0 += 8) {
-        float4 v[8];
+    for (int j = 0; j < L; j++) { sum[j] = 0.0; mag[j] = 0.0; mn[j] = ext_empty<AMD64>(); mx[j] = mn[j]; }
+    if (rec * REC_VECS < n_vecs) {
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+            float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = v0 + i0 + i < n_vecs ? __ldcs(data + v0 + i0 + i) : make_float4(0, 0, 0, 0);
+            for (int i = 0; i < 8; i++) v[i] = v0 + i0 + i < n_vecs ? __ldcs(data + v0 + i0 + i) : make_float4(0, 0, 0, 0);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (v0 + i0 + i >= n_vecs) break;
-            const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            for (int i = 0; i < 8; i++) {
+                if (v0 + i0 + i >= n_vecs) break;
+                const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int s = AMD64 ? j : 0;
-                const double t = stat_term<MODE>(e[j], mean);
-                sum[s] = __dadd_rn(sum[s], t);
-                mag[s] = __dadd_rn(mag[s], fabs(t));
-                if (MODE == 0) { mn[s] = ext_push<AMD64, false>(mn[s], e[j]); mx[s] = ext_push<AMD64, true>(mx[s], e[j]); }
+                for (int j = 0; j < 4; j++) {
+                    const int s = AMD64 ? j : 0;
+                    const double t = stat_term<MODE>(e[j], mean);
+                    sum[s] = __dadd_rn(sum[s], t);
+                    mag[s] = __dadd_rn(mag[s], fabs(t));
+                    if (MODE == 0) { mn[s] = ext_push<AMD64, false>(mn[s], e[j]); mx[s] = ext_push<AMD64, true>(mx[s], e[j]); }
+                }
             }
         }
     }
-    // ordered tree over the 32 threads of the record (thread t holds the part before thread t+1's)
+    // ordered tree over the 32 threads of the warp (thread t holds the part before thread t+1's)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
@@ -186,57 +241,127 @@ __global__ void __launch_bounds__(256) stats_records_kernel(const float4 *__rest
         }
     }
     if (lane == 0) {
-        StatRec r;
+        long long vecs = n_vecs - rec * REC_VECS;
+        vecs = vecs < 0 ? 0 : (vecs > REC_VECS ? REC_VECS : vecs);
+        const double len = (double)(AMD64 ? vecs : 4 * vecs);
+        sh_len[warp] = len;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int s = j < L ? j : 0;
-            r.sum[j] = j < L ? sum[s] : 0.0; r.mag[j] = j < L ? mag[s] : 0.0;
-            r.mn[j] = j < L ? mn[s] : Ext{NAN, 2}; r.mx[j] = j < L ? mx[s] : Ext{NAN, 2};
+            sh_S[j][warp] = j < L ? sum[s] : 0.0;
+            sh_A[j][warp] = j < L ? len * mag[s] : 0.0;
+            sh_mn[j][warp] = j < L ? mn[s] : ext_empty<AMD64>();
+            sh_mx[j][warp] = j < L ? mx[s] : ext_empty<AMD64>();
         }
-        recs[rec] = r;
     }
-}
-
-struct StatFold {           // per lane: the parallel sum, the bound on the sequential chain's distance from it, extremes
-    double sum[4], bound[4];
-    float mn[4], mx[4];
-};
-
-// Folds the records in order: 4 lanes x 32 workers, each worker a contiguous run of records.
-// chain_len = elements one record adds to a chain (1024 per lane, or 4096 for the single chain).
-template <bool AMD64>
-__global__ void __launch_bounds__(128) stats_fold_kernel(const StatRec *__restrict__ recs, int n_recs, double chain_len,
-                                                         StatFold *__restrict__ out) {
-    __shared__ double w_sum[4][32], w_wsum[4][32], w_len[4][32];
-    __shared__ Ext w_mn[4][32], w_mx[4][32];
-    const int j = threadIdx.x >> 5, k = threadIdx.x & 31;
-    const int per = (n_recs + 31) / 32;
-    const int lo = k * per, hi = min(n_recs, lo + per);
-    double prefix = 0.0, weighted = 0.0;      // weighted = sum over records of chain_len * (|local prefix| + magnitudes)
-    Ext mn{AMD64 ? 0.0f : NAN, 2}, mx = mn;
-    for (int c = lo; c < hi; c++) {
-        weighted += chain_len * (fabs(prefix) + recs[c].mag[j]);
-        prefix += recs[c].sum[j];
-        mn = ext_join<AMD64, false>(mn, recs[c].mn[j]);
-        mx = ext_join<AMD64, true>(mx, recs[c].mx[j]);
-    }
-    w_sum[j][k] = prefix; w_wsum[j][k] = weighted; w_len[j][k] = chain_len * (double)max(hi - lo, 0);
-    w_mn[j][k] = mn; w_mx[j][k] = mx;
     __syncthreads();
-    if (k == 0) {
-        double total = 0.0, bound = 0.0;
-        Ext tmn{AMD64 ? 0.0f : NAN, 2}, tmx = tmn;
-        for (int q = 0; q < 32; q++) {
-            bound += w_wsum[j][q] + w_len[j][q] * fabs(total);
-            total += w_sum[j][q];
-            tmn = ext_join<AMD64, false>(tmn, w_mn[j][q]);
-            tmx = ext_join<AMD64, true>(tmx, w_mx[j][q]);
+    if (threadIdx.x < 4) {                       // the eight warps of this CTA, in order, into one node
+        const int j = threadIdx.x;
+        double S = 0.0, A = 0.0, len = 0.0;
+        Ext tmn = ext_empty<AMD64>(), tmx = tmn;
+        for (int w = 0; w < 8; w++) {
+            A += sh_A[j][w] + sh_len[w] * fabs(S);
+            S += sh_S[j][w];
+            len += sh_len[w];
+            tmn = ext_join<AMD64, false>(tmn, sh_mn[j][w]);
+            tmx = ext_join<AMD64, true>(tmx, sh_mx[j][w]);
         }
-        out->sum[j] = total;
-        // u = 2^-53 per rounded addition of the reference's chain; the same order of error again for this
-        // kernel's own float64 sums (each shorter than one record), and head-room for second-order terms
-        out->bound[j] = bound * (2.0 * 1.001 * 1.1102230246251565e-16);
-        out->mn[j] = tmn.c; out->mx[j] = tmx.c;
+        Node *nd = nodes + blockIdx.x;
+        nd->S[j] = S; nd->A[j] = A; nd->mn[j] = tmn; nd->mx[j] = tmx;
+        if (j == 0) nd->len = len;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // the last CTA: nodes in order, 64 workers x 4 lanes, then an ordered tree over the workers
+    {
+        const int j = threadIdx.x & 3, k = threadIdx.x >> 2;
+        const int n_nodes = (int)gridDim.x;
+        const int per = (n_nodes + FOLD_WORKERS - 1) / FOLD_WORKERS;
+        const int lo = min(n_nodes, k * per), hi = min(n_nodes, lo + per);
+        double S = 0.0, A = 0.0, len = 0.0;
+        Ext tmn = ext_empty<AMD64>(), tmx = tmn;
+        const volatile Node *vn = nodes;
+        for (int c = lo; c < hi; c++) {
+            const double cS = vn[c].S[j], cA = vn[c].A[j], cl = vn[c].len;
+            Ext cmn, cmx;
+            cmn.c = vn[c].mn[j].c; cmn.kind = vn[c].mn[j].kind; cmx.c = vn[c].mx[j].c; cmx.kind = vn[c].mx[j].kind;
+            A += cA + cl * fabs(S);
+            S += cS;
+            len += cl;
+            tmn = ext_join<AMD64, false>(tmn, cmn);
+            tmx = ext_join<AMD64, true>(tmx, cmx);
+        }
+        sh_S[j][k] = S; sh_A[j][k] = A; sh_mn[j][k] = tmn; sh_mx[j][k] = tmx;
+        if (j == 0) sh_len[k] = len;
+        __syncthreads();
+        for (int d = 1; d < FOLD_WORKERS; d <<= 1) {
+            double nS = 0, nA = 0, nl = 0;
+            Ext nmn = tmn, nmx = tmx;
+            const bool act = (k % (2 * d)) == 0;
+            if (act) {
+                nA = sh_A[j][k] + sh_A[j][k + d] + sh_len[k + d] * fabs(sh_S[j][k]);
+                nS = sh_S[j][k] + sh_S[j][k + d];
+                nl = sh_len[k] + sh_len[k + d];
+                nmn = ext_join<AMD64, false>(sh_mn[j][k], sh_mn[j][k + d]);
+                nmx = ext_join<AMD64, true>(sh_mx[j][k], sh_mx[j][k + d]);
+            }
+            __syncthreads();
+            if (act) {
+                sh_S[j][k] = nS; sh_A[j][k] = nA; sh_mn[j][k] = nmn; sh_mx[j][k] = nmx;
+                if (j == 0) sh_len[k] = nl;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x != 0) return;
+    *counter = 0;                                              // ready for the next pass
+    // the lanes, folded like stats_amd64.s:80-84; the interval around the total
+    double total = (sh_S[2][0] + sh_S[3][0]) + (sh_S[0][0] + sh_S[1][0]);
+    double bound = 0.0, m = 0.0;
+    for (int j = 0; j < 4; j++) { bound += sh_A[j][0]; m += fabs(sh_S[j][0]); }
+    // u = 2^-53 per rounded addition of the reference's chain; as much again for this kernel's own float64 sums
+    // (every one of them shorter than a leaf), head-room for second-order terms; then the three folding additions
+    bound *= 2.0 * 1.001 * 1.1102230246251565e-16;
+    bound += 8.0 * 2.220446049250313e-16 * (m + bound);
+    bound = bound * 1.000001 + 2.2250738585072014e-308;
+    out->total[MODE] = total;
+    out->bound[MODE] = bound;
+    const double dn = (double)n;
+    const int n_tail = AMD64 ? 0 : (int)(n - 4 * n_vecs);       // a ragged pure-Go array: its last elements continue the chain
+    const float *tail = reinterpret_cast<const float *>(data) + 4 * n_vecs;
+    double lo = total - bound, hi = total + bound;
+    if (MODE == 1 && lo < 0.0) lo = 0.0;
+    for (int i = 0; i < n_tail; i++) {
+        const double t = stat_term<MODE>(tail[i], mean);
+        lo = __dadd_rn(lo, t); hi = __dadd_rn(hi, t);
+    }
+    if (MODE == 0) {
+        const float mlo = __double2float_rn(__ddiv_rn(lo, dn)), mhi = __double2float_rn(__ddiv_rn(hi, dn));
+        out->mean = mlo;
+        out->mean_decided = bound == bound && dev_f32_bits(mlo) == dev_f32_bits(mhi);
+        float mn_, mx_;
+        if (AMD64) {
+            // stats_amd64.s:66-77: lanes (0,1) and (2,3), then across; src1 is the lower lane
+            mn_ = minps(minps(sh_mn[0][0].c, sh_mn[1][0].c), minps(sh_mn[2][0].c, sh_mn[3][0].c));
+            mx_ = maxps(maxps(sh_mx[0][0].c, sh_mx[1][0].c), maxps(sh_mx[2][0].c, sh_mx[3][0].c));
+        } else {
+            // stats.go:265-273: the loop starts from data[0] (a NaN there stays) and the tail continues it
+            Ext a = sh_mn[0][0], b = sh_mx[0][0];
+            for (int i = 0; i < n_tail; i++) { a = ext_push<false, false>(a, tail[i]); b = ext_push<false, true>(b, tail[i]); }
+            const float first = reinterpret_cast<const float *>(data)[0];
+            mn_ = first != first ? first : a.c;
+            mx_ = first != first ? first : b.c;
+        }
+        out->mn = mn_; out->mx = mx_;
+    } else {
+        const float slo = __double2float_rn(__dsqrt_rn(__ddiv_rn(lo, dn))), shi = __double2float_rn(__dsqrt_rn(__ddiv_rn(hi, dn)));
+        out->stddev = slo;                                      // stats.go:147-149
+        out->std_decided = bound == bound && dev_f32_bits(slo) == dev_f32_bits(shi);
     }
 }
 
@@ -317,127 +442,90 @@ __global__ void __launch_bounds__(256) outlier_scan_kernel(const float *__restri
 
 // ---- host side ---------------------------------------------------------------------------------
 
-static inline uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-// sum of the four lane sums in the kernels' fold order, and the width of the interval around it
-static void fold_lanes(const StatFold &f, double *total, double *bound) {
-    const double t = (f.sum[2] + f.sum[3]) + (f.sum[0] + f.sum[1]);
-    double b = 0.0, m = 0.0;
-    for (int j = 0; j < 4; j++) { b += f.bound[j]; m += fabs(f.sum[j]); }
-    b += 8.0 * DBL_EPSILON * (m + b);          // the three folding additions, on both sides
-    *total = t;
-    *bound = b * 1.000001 + DBL_MIN;
-}
-
-// Launches one pass (MODE 0: sums + extremes; MODE 1: squared deviations) over n elements and returns
-// the reference's chain total: proven from the interval when `resolve` accepts both ends, else replayed.
-template <int MODE, typename Resolve>
-static int stats_pass(nl_ctx *ctx, const float *dev, long long n, bool amd64, float mean, StatFold *fold_host, double *total,
-                      Resolve same_result) {
-    const long long n_vecs = n / 4;
-    const int n_recs = (int)((n_vecs + REC_VECS - 1) / REC_VECS);
-    const size_t rec_bytes = ((size_t)n_recs * sizeof(StatRec) + 255) & ~(size_t)255;
-    int rc = ensure_scratch(ctx, rec_bytes + 512);
-    if (rc != NL_OK) return rc;
-    StatRec *recs = (StatRec *)ctx->scratch;
-    StatFold *fold = (StatFold *)((char *)ctx->scratch + rec_bytes);
-    double *exact = (double *)((char *)fold + 256);
-    const unsigned grid = (unsigned)((n_recs + 7) / 8);
-    const float4 *d4 = (const float4 *)dev;
-    if (amd64) {
-        stats_records_kernel<true, MODE><<<grid, 256, 0, ctx->stream>>>(d4, n_vecs, mean, recs);
-        stats_fold_kernel<true><<<1, 128, 0, ctx->stream>>>(recs, n_recs, (double)REC_VECS, fold);
-    } else {
-        stats_records_kernel<false, MODE><<<grid, 256, 0, ctx->stream>>>(d4, n_vecs, mean, recs);
-        stats_fold_kernel<false><<<1, 128, 0, ctx->stream>>>(recs, n_recs, 4.0 * REC_VECS, fold);
-    }
-    NL_CUDA(cudaGetLastError());
-    ctx->launches += 2;
-    NL_CUDA(cudaMemcpyAsync(fold_host, fold, sizeof(StatFold), cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    double t, b;
-    fold_lanes(*fold_host, &t, &b);
-    if (b == b && same_result(t - b, t + b)) { *total = t; return NL_OK; }
-    if (amd64) stats_exact_kernel<true, MODE><<<1, 32, 0, ctx->stream>>>(d4, n_vecs, mean, exact);
-    else stats_exact_kernel<false, MODE><<<1, 32, 0, ctx->stream>>>(d4, n_vecs, mean, exact);
-    NL_CUDA(cudaGetLastError());
-    ctx->launches++;
-    ctx->exact_replays++;
-    double lanes[4];
-    NL_CUDA(cudaMemcpyAsync(lanes, exact, sizeof(lanes), cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    *total = amd64 ? (lanes[2] + lanes[3]) + (lanes[0] + lanes[1]) : lanes[0];
-    return NL_OK;
-}
-
-// Stats.Min / Mean / Max / StdDev of n device floats -> out = {min, mean, max, stddev}
+// Stats.Min / Mean / Max / StdDev of n device floats -> out = {min, mean, max, stddev}.
+// Both passes are queued back to back (the second reads the mean the first one left on the device); one read-back.
+// An undecided interval replays that chain in order and, for the mean, repeats the second pass.
 static int stats_dev(nl_ctx *ctx, const float *dev, long long n, float out[4]) {
     NL_REQUIRE(n >= 1, "statistics of an empty array");
     NL_REQUIRE(n < ((long long)1 << 40), "array too long");
     // the AVX2 loops read whole vectors; a length that is not a multiple of four makes the reference read past
     // its slice, so such arrays take the pure-Go definition (as do all arrays in pure-Go numerics)
     const bool amd64 = ctx->numerics == NL_NUMERICS_AMD64 && n % 4 == 0;
-    const double dn = (double)n;
-    StatFold f;
-    double total = 0.0;
-    // a tail of n % 4 elements only exists in pure-Go numerics; it is appended to the single chain on the host
-    float tail[3] = {0, 0, 0};
-    const int n_tail = (int)(n % 4);
-    if (n_tail) {
-        NL_CUDA(cudaMemcpyAsync(tail, dev + (n - n_tail), sizeof(float) * n_tail, cudaMemcpyDeviceToHost, ctx->stream));
-        NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    float first = 0.0f;
-    NL_CUDA(cudaMemcpyAsync(&first, dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-
-    // a tail changes the chain's last few additions: the interval test would need them too, so arrays with a
-    // tail fold it in exactly here, after an exact or proven body
-    auto finish_sum = [&](double body, int mode, float mean) {
-        for (int i = 0; i < n_tail; i++) {
-            if (mode == 0) body += (double)tail[i];
-            else { volatile float d = tail[i] - mean; const double dd = (double)d; volatile double sq = dd * dd; body += sq; }
-        }
-        return body;
+    const long long n_vecs = n / 4;
+    const int n_tail = (int)(n - 4 * n_vecs);
+    const unsigned grid = (unsigned)std::max<long long>(1, (n_vecs + 8 * REC_VECS - 1) / (8 * REC_VECS));
+    const size_t node_bytes = ((size_t)grid * sizeof(Node) + 255) & ~(size_t)255;
+    int rc = ensure_scratch(ctx, node_bytes + 1024);
+    if (rc != NL_OK) return rc;
+    Node *nodes = (Node *)ctx->scratch;
+    StatOut *dout = (StatOut *)((char *)ctx->scratch + node_bytes);
+    unsigned *counter = (unsigned *)((char *)dout + 256);
+    double *exact = (double *)((char *)dout + 512);
+    const float4 *d4 = (const float4 *)dev;
+    NL_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
+    auto pass0 = [&]() {
+        if (amd64) stats_pass_kernel<true, 0><<<grid, 256, 0, ctx->stream>>>(d4, n_vecs, n, nodes, counter, dout);
+        else stats_pass_kernel<false, 0><<<grid, 256, 0, ctx->stream>>>(d4, n_vecs, n, nodes, counter, dout);
+        ctx->launches++;
     };
-    auto mean_of = [&](double s) { return (float)(s / dn); };
-    int rc;
-    if (n >= 4) {
-        rc = stats_pass<0>(ctx, dev, n - n_tail, amd64, 0.0f, &f, &total, [&](double lo, double hi) {
-            return f32_bits(mean_of(finish_sum(lo, 0, 0.0f))) == f32_bits(mean_of(finish_sum(hi, 0, 0.0f)));
-        });
-        if (rc != NL_OK) return rc;
-    } else {
-        for (int j = 0; j < 4; j++) { f.mn[j] = NAN; f.mx[j] = NAN; }
-    }
-    const float mean = mean_of(finish_sum(total, 0, 0.0f));
-    float mn, mx;
-    if (amd64) {
-        // stats_amd64.s:66-77: lanes (0,1) and (2,3), then across; src1 is the lower lane
-        auto mnps = [](float a, float b) { return a < b ? a : b; };
-        auto mxps = [](float a, float b) { return a > b ? a : b; };
-        mn = mnps(mnps(f.mn[0], f.mn[1]), mnps(f.mn[2], f.mn[3]));
-        mx = mxps(mxps(f.mx[0], f.mx[1]), mxps(f.mx[2], f.mx[3]));
-    } else {
-        // stats.go:265-273: starts from data[0]; a NaN there stays; the tail continues the same loop
-        mn = f.mn[0]; mx = f.mx[0];
-        for (int i = 0; i < n_tail; i++) {
-            if (tail[i] == tail[i] && (mn != mn || tail[i] < mn)) mn = tail[i];
-            if (tail[i] == tail[i] && (mx != mx || tail[i] > mx)) mx = tail[i];
+    auto pass1 = [&]() {
+        if (amd64) stats_pass_kernel<true, 1><<<grid, 256, 0, ctx->stream>>>(d4, n_vecs, n, nodes, counter, dout);
+        else stats_pass_kernel<false, 1><<<grid, 256, 0, ctx->stream>>>(d4, n_vecs, n, nodes, counter, dout);
+        ctx->launches++;
+    };
+    // the chain of pass `mode` replayed in order (plus the tail of a ragged pure-Go array, on the host)
+    float tail[3] = {0, 0, 0};
+    auto replay = [&](int mode, float mean, double *total) -> int {
+        if (amd64) {
+            if (mode == 0) stats_exact_kernel<true, 0><<<1, 32, 0, ctx->stream>>>(d4, n_vecs, mean, exact);
+            else stats_exact_kernel<true, 1><<<1, 32, 0, ctx->stream>>>(d4, n_vecs, mean, exact);
+        } else {
+            if (mode == 0) stats_exact_kernel<false, 0><<<1, 32, 0, ctx->stream>>>(d4, n_vecs, mean, exact);
+            else stats_exact_kernel<false, 1><<<1, 32, 0, ctx->stream>>>(d4, n_vecs, mean, exact);
         }
-        if (first != first) mn = mx = first;
-    }
-    double var_total = 0.0;
-    auto std_of = [&](double s) { return (float)sqrt(s / dn); };
-    if (n >= 4) {
-        StatFold fv;
-        rc = stats_pass<1>(ctx, dev, n - n_tail, amd64, mean, &fv, &var_total, [&](double lo, double hi) {
-            return f32_bits(std_of(finish_sum(lo < 0.0 ? 0.0 : lo, 1, mean))) == f32_bits(std_of(finish_sum(hi, 1, mean)));
-        });
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        ctx->exact_replays++;
+        double lanes[4];
+        NL_CUDA(cudaMemcpyAsync(lanes, exact, sizeof(lanes), cudaMemcpyDeviceToHost, ctx->stream));
+        if (n_tail) NL_CUDA(cudaMemcpyAsync(tail, dev + 4 * n_vecs, sizeof(float) * n_tail, cudaMemcpyDeviceToHost, ctx->stream));
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+        double t = amd64 ? (lanes[2] + lanes[3]) + (lanes[0] + lanes[1]) : lanes[0];
+        for (int i = 0; i < n_tail; i++) {
+            if (mode == 0) t += (double)tail[i];
+            else { volatile float d = tail[i] - mean; const double dd = (double)d; volatile double sq = dd * dd; t += sq; }
+        }
+        *total = t;
+        return NL_OK;
+    };
+    pass0();
+    pass1();
+    NL_CUDA(cudaGetLastError());
+    StatOut h;
+    NL_CUDA(cudaMemcpyAsync(&h, dout, sizeof(StatOut), cudaMemcpyDeviceToHost, ctx->stream));
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double dn = (double)n;
+    if (!h.mean_decided) {
+        double t;
+        rc = replay(0, 0.0f, &t);
         if (rc != NL_OK) return rc;
+        h.mean = (float)(t / dn);
+        NL_CUDA(cudaMemcpyAsync(&dout->mean, &h.mean, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        pass1();
+        NL_CUDA(cudaGetLastError());
+        const float mean = h.mean;
+        NL_CUDA(cudaMemcpyAsync(&h, dout, sizeof(StatOut), cudaMemcpyDeviceToHost, ctx->stream));
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+        h.mean = mean;
     }
-    out[0] = mn; out[1] = mean; out[2] = mx;
-    out[3] = std_of(finish_sum(var_total, 1, mean));       // stats.go:147-149
+    if (!h.std_decided) {
+        double t;
+        rc = replay(1, h.mean, &t);
+        if (rc != NL_OK) return rc;
+        h.stddev = (float)sqrt(t / dn);
+    }
+    out[0] = h.mn; out[1] = h.mean; out[2] = h.mx; out[3] = h.stddev;
     return NL_OK;
 }
 
@@ -571,6 +659,27 @@ int nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t w
                               : cuda_fail(e, "bad-pixel map upload");
     cudaFree(dev);
     return rc;
+}
+
+// OpBadPixel.Apply for monochrome frames, preprocess.go:180-191: BadPixelMap on the device, then the listed pixels
+// repaired in place (sparse and sequential: on the host).  host_data is updated; *removed = len(bpm).
+int nl_op_bad_pixel(nl_ctx *ctx, float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
+                    int64_t *removed, float stats[4]) {
+    NL_REQUIRE(ctx && host_data && removed && stats && len >= 1 && width > 0, "bad argument");
+    *removed = 0;
+    if (sigma_low == 0.0f || sigma_high == 0.0f) return NL_OK;          // :181-183
+    int64_t cap = len / 100 + 1024, count = 0;                          // badpixels.go:42
+    std::vector<int32_t> bpm((size_t)cap);
+    int rc = nl_bad_pixel_map(ctx, host_data, len, width, sigma_low, sigma_high, bpm.data(), cap, &count, stats);
+    if (rc == NL_OK && count > cap) {
+        cap = count;
+        bpm.resize((size_t)cap);
+        rc = nl_bad_pixel_map(ctx, host_data, len, width, sigma_low, sigma_high, bpm.data(), cap, &count, stats);
+    }
+    if (rc != NL_OK) return rc;
+    median_filter_sparse_host(host_data, (int32_t)len, width, bpm.data(), count);
+    *removed = count;
+    return NL_OK;
 }
 
 }  // extern "C"

@@ -237,6 +237,22 @@ static int reject_bad_pixels(nl_star *stars, int n, const float *data, int32_t l
     return remaining;
 }
 
+// pre.MedianFilterSparse, badpixels.go:79-85: the listed pixels are replaced one after the other, in place, by the
+// median of their radius-1.5 neighbourhood (a repaired pixel is seen by the repairs after it); sparse, host side
+void median_filter_sparse_host(float *data, int32_t len, int32_t width, const int32_t *indices, int64_t n) {
+    const std::vector<int32_t> mask = create_mask(width, 1.5f);
+    float buffer[16] = {0};
+    for (int64_t k = 0; k < n; k++) {
+        const int32_t i = indices[k];
+        int num = 0;
+        for (int32_t o : mask) {
+            const int32_t io = i + o;
+            if (io >= 0 && io < len) buffer[num++] = data[io];
+        }
+        data[i] = median9(buffer);
+    }
+}
+
 // QSortStarsDesc, star/qsort.go:25-55: unstable Hoare quicksort by mass, descending
 static void qsort_stars_desc(nl_star *a, int n) {
     while (n > 1) {

@@ -191,6 +191,16 @@ def bad_pixel_map(ctx: B.Context, data, width, sigma_low, sigma_high, cap=None):
         cap = n.value
 
 
+def op_bad_pixel(ctx: B.Context, data, width, sigma_low, sigma_high):
+    """OpBadPixel.Apply, monochrome (preprocess.go:180-191) -> (repaired data, number removed, medianDiffStats[4])"""
+    data = np.array(data, dtype=np.float32).reshape(-1)          # a copy: the operator repairs in place
+    st = np.zeros(4, dtype=np.float32)
+    n = C.c_int64()
+    check(load_library().nl_op_bad_pixel(ctx.handle, data.ctypes.data_as(C.c_void_p), data.size, int(width), float(sigma_low),
+                                         float(sigma_high), C.byref(n), st.ctypes.data_as(C.POINTER(C.c_float))))
+    return data, n.value, st
+
+
 def estimate_noise(ctx: B.Context, data, width):
     """stats.EstimateNoise (noise_amd64.go:25-43, or noise.go:24-55 in pure-Go numerics) of one frame -> float32"""
     data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)

@@ -121,6 +121,10 @@ void   nlo_median_filter3x3(float *out, const float *data, int32_t width, int32_
 int64_t nlo_bad_pixel_map(const float *data, int64_t len, int32_t width, float sigma_low, float sigma_high, int amd64,
                           float *tmp, int32_t *bpm, int64_t cap, float stats[4]);
 
+void   nlo_median_filter_sparse(float *data, int32_t len, int32_t width, const int32_t *indices, int64_t n);
+int64_t nlo_op_bad_pixel(float *data, int64_t len, int32_t width, float sigma_low, float sigma_high, int amd64,
+                         float *tmp, int32_t *bpm, float stats[4]);
+
 /* ---- internal/star/findstars.go, internal/star/qsort.go ---- */
 int   nlo_find_bright_pixels(const float *data, int32_t len, int32_t width, float threshold, int32_t radius,
                              nlo_star *stars, int cap);

@@ -242,3 +242,21 @@ int64_t nlo_bad_pixel_map(const float *data, int64_t len, int32_t width, float s
     }
     return count;
 }
+
+/* pre.MedianFilterSparse, badpixels.go:79-85 (in place, in list order) with the radius-1.5 mask of
+ * OpBadPixel.Apply (preprocess.go:188-189) */
+void nlo_median_filter_sparse(float *data, int32_t len, int32_t width, const int32_t *indices, int64_t n) {
+    int32_t mask[16];
+    int nmask = nlo_create_mask(width, 1.5f, mask, 16);
+    float buffer[16] = {0};
+    for (int64_t k = 0; k < n; k++) data[indices[k]] = nlo_gather_and_median(data, len, indices[k], mask, nmask, buffer);
+}
+
+/* OpBadPixel.Apply, monochrome path (preprocess.go:180-191).  Returns the number of repaired pixels. */
+int64_t nlo_op_bad_pixel(float *data, int64_t len, int32_t width, float sigma_low, float sigma_high, int amd64,
+                         float *tmp, int32_t *bpm, float stats[4]) {
+    if (sigma_low == 0.0f || sigma_high == 0.0f) return 0;
+    int64_t n = nlo_bad_pixel_map(data, len, width, sigma_low, sigma_high, amd64, tmp, bpm, len, stats);
+    nlo_median_filter_sparse(data, (int32_t)len, width, bpm, n);
+    return n;
+}

@@ -91,6 +91,8 @@ def lib():
         L.nlo_bad_pixel_map.restype = C.c_int64
         L.nlo_bad_pixel_map.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int, fp,
                                         C.POINTER(C.c_int32), C.c_int64, fp]
+        L.nlo_op_bad_pixel.restype = C.c_int64
+        L.nlo_op_bad_pixel.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int, fp, C.POINTER(C.c_int32), fp]
         L.nlo_calc_variance_avx2.restype = C.c_double
         L.nlo_calc_variance_avx2.argtypes = [fp, C.c_int64, C.c_float]
         L.nlo_calc_min_mean_max_avx2.argtypes = [fp, C.c_int64, fp, fp, fp]
@@ -255,3 +257,14 @@ def synth_frame(p0, length, k, seed=12345):
 
 def synth_frames(n, p0, length, seed=12345):
     return np.stack([synth_frame(p0, length, k, seed) for k in range(n)])
+
+
+def op_bad_pixel(data, width, sigma_low, sigma_high, amd64=True):
+    """OpBadPixel.Apply (monochrome) -> (repaired data, number removed, medianDiffStats)"""
+    data = np.array(data, dtype=np.float32).ravel()
+    tmp = np.empty_like(data)
+    bpm = np.empty(data.size, np.int32)
+    st = np.zeros(4, np.float32)
+    n = lib().nlo_op_bad_pixel(_fp(data), data.size, int(width), float(sigma_low), float(sigma_high), int(amd64),
+                               _fp(tmp), bpm.ctypes.data_as(C.POINTER(C.c_int32)), _fp(st))
+    return data, int(n), st

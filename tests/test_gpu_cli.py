@@ -87,3 +87,23 @@ def test_stack_of_stacks_and_errors(frames_dir):
     assert r.returncode == 1 and "invalid stacking mode" in r.stdout
     r = subprocess.run([NLSTACK, "stack", "-stMode", "4", "-stWeight", "1", "-out", out] + files[:6], capture_output=True, text=True)
     assert r.returncode == 1 and "MADSigma stacking with weights" in r.stdout
+
+
+def test_stars_verb_with_bad_pixel_repair(tmp_path):
+    """`nlstack stars -bpSigLow 3 -bpSigHigh 5 -starBpSig 5`: OpBadPixel (BadPixelMap on the device + in-order sparse
+    repair) leaves the frame's MedianDiffStats, whose StdDev is star detection's bad-pixel scale"""
+    from test_gpu_project_stars import star_field
+    w, h = 640, 480
+    img = star_field(w, h, 30, seed=12, hot=60)
+    path = str(tmp_path / "field.fits")
+    write_fits(path, img.reshape(h, w), -32)
+    loc, scale = float(np.float32(np.median(img))), 3.0
+    log = run(["stars", "-bpSigLow", "3", "-bpSigHigh", "5", "-starBpSig", "5", "-starSig", "10", "-starRadius", "12",
+               "-loc", repr(loc), "-scale", repr(scale), path])
+    fixed, removed, st = O.op_bad_pixel(img, w, 3.0, 5.0, amd64=True)
+    stars, _, hfr = O.find_stars(fixed, w, np.float32(loc), np.float32(scale), 10.0, 5.0, 1.4, 12, float(st[3]))
+    m = re.search(r"Removed (\d+) bad pixels \(([\d.]+)%\) with sigma low=3.00 high=5.00", log)
+    assert m and int(m.group(1)) == removed and removed > 20
+    m = re.search(r"Stars (\d+) HFR ([\d.]+)", log)
+    assert m and int(m.group(1)) == len(stars) and len(stars) > 5
+    assert m.group(2) == "%.2f" % float(hfr)

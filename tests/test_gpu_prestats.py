@@ -113,6 +113,23 @@ def test_bad_pixel_map_truncated_list_still_counts(ctx):
     assert np.array_equal(full, part) and len(full) > 5
 
 
+def test_op_bad_pixel_repairs_in_list_order(ctx, numerics):
+    """OpBadPixel.Apply: hot pixel clusters make the in-place, in-order repair observable"""
+    w, h = 320, 200
+    img = frame(w, h, 21)
+    rng = np.random.default_rng(4)
+    for _ in range(30):                       # 2x2 hot clusters: a repair sees the repair before it
+        y, x = int(rng.integers(1, h - 2)), int(rng.integers(1, w - 2))
+        img[y:y + 2, x:x + 2] += np.float32(4000)
+    got, n, st = nl.op_bad_pixel(ctx, img, w, 3.0, 5.0)
+    want, wn, wst = O.op_bad_pixel(img, w, 3.0, 5.0, amd64=numerics)
+    assert n == wn and n >= 100
+    assert np.array_equal(st.view(np.uint32), wst.view(np.uint32))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    same, n0, _ = nl.op_bad_pixel(ctx, img, w, 0.0, 5.0)          # a zero sigma switches the operator off
+    assert n0 == 0 and np.array_equal(same, img.ravel())
+
+
 def test_star_detection_threshold_from_device_stats(ctx):
     """medianDiffStats.StdDev() of BadPixelMap is what FindStars takes as its bad-pixel scale (findstars.go:134-169):
     the whole detection input now comes from the device"""

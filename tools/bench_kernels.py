@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="smaller inputs (for ncu)")
-    ap.add_argument("--only", default="", help="comma list: mean,mean_w,median,sigma,sigma_w,winsor,winsor_w,mad,linfit,project,bright,incremental")
+    ap.add_argument("--only", default="", help="comma list: mean,mean_w,median,sigma,sigma_w,winsor,winsor_w,mad,linfit,project,fits,bright,prestats,incremental")
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     import torch
@@ -159,6 +159,45 @@ def main():
         report("find_bright (2 scans + offsets + D2H of candidates)", "%dx%d, radius 16, %d candidates, L2 flushed" % (w, h, cnt.value),
                4.0 * w * h, ms, {"mpx_per_s": w * h / ms / 1e3, "note": "whole call incl. host sync; the image is read twice (count, write)"})
         del img
+
+    # ---- N2 / N3: frame statistics (noise estimate, 3x3 median filter, min/mean/max/stddev, bad-pixel map) ----
+    if not only or "prestats" in only:
+        w, h = (3000, 2000) if args.quick else (6000, 4000)
+        g = torch.Generator(device=dev).manual_seed(11)
+        img = torch.randn(w * h, dtype=torch.float32, device=dev, generator=g) * 30 + 1000
+        img += (torch.rand(w * h, device=dev, generator=g) < 2e-4).float() * 5000
+        tmp = torch.empty_like(img)
+        st = (C.c_float * 4)()
+        one = (C.c_float * 1)()
+        for numerics, tag in ((nl.NUMERICS_AMD64, "amd64"), (nl.NUMERICS_PUREGO, "purego")):
+            ctx.set_numerics(numerics)
+            ms = timed(lambda: nl.binding.check(lib.nl_estimate_noise_dev(ctx.handle, C.c_void_p(img.data_ptr()), 1, w * h, w, h, one)))
+            report("estimate_noise (%s order; rows kernel + finalize + D2H)" % tag, "%dx%d, L2 flushed" % (w, h), 4.0 * w * h, ms)
+            ms = timed(lambda: nl.binding.check(lib.nl_median_filter3x3_dev(ctx.handle, C.c_void_p(img.data_ptr()), w, h, C.c_void_p(tmp.data_ptr()))))
+            report("median3x3_kernel (%s)" % tag, "%dx%d, L2 flushed" % (w, h), 8.0 * w * h, ms)
+            r0 = ctx.exact_replays()
+            ms = timed(lambda: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(tmp.data_ptr()), w * h, st)))
+            report("stats min/mean/max/stddev (%s; 2 fused passes, one read-back)" % tag, "%dx%d, L2 flushed" % (w, h), 8.0 * w * h, ms,
+                   {"exact_replays": ctx.exact_replays() - r0})
+            cap = w * h // 50
+            bpm = np.empty(cap, dtype=np.int32)
+            cnt = C.c_int64()
+            ms = timed(lambda: nl.binding.check(lib.nl_bad_pixel_map_dev(ctx.handle, C.c_void_p(img.data_ptr()), w * h, w, 3.0, 5.0,
+                                                                         C.c_void_p(tmp.data_ptr()), bpm.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                                         cap, C.byref(cnt), st)))
+            report("bad_pixel_map whole call (%s; median-diff, stats, 2 scans)" % tag, "%dx%d, %d bad pixels, L2 flushed" % (w, h, cnt.value),
+                   24.0 * w * h, ms)
+        ctx.set_numerics(nl.NUMERICS_AMD64)
+        # the in-order replay of the float64 chains (taken when the interval test cannot decide): force it with a NaN-free
+        # frame whose sum is steered onto a rounding boundary is data-dependent, so time the kernel through its worst case:
+        # a frame containing one NaN makes every interval test fail
+        img2 = img.clone()
+        img2[12345] = float("nan")
+        r0 = ctx.exact_replays()
+        ms = timed(lambda: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(img2.data_ptr()), w * h, st)), reps=3, warm=1)
+        report("stats with both chains replayed in order (worst case)", "%dx%d" % (w, h), 8.0 * w * h, ms,
+               {"exact_replays": ctx.exact_replays() - r0})
+        del img, tmp, img2
 
     # ---- stack-of-stacks accumulate -----------------------------------------------------------------
     if not only or "incremental" in only:
