@@ -178,6 +178,15 @@ int  nl_project_scaled(nl_ctx *ctx, const float *host_src, int32_t src_w, int32_
                        int32_t dst_h, const float trans[6], float out_of_bounds, float multiplier, float offset);
 int  nl_project_scaled_dev(nl_ctx *ctx, const float *dev_src, int32_t src_w, int32_t src_h, float *dev_dst, int32_t dst_w,
                            int32_t dst_h, const float trans[6], float out_of_bounds, float multiplier, float offset);
+/* Frame-sharded resample feeding row-sharded stacking.  Resamples one frame like
+ * nl_project_scaled_dev (multiplier 1, offset 0 = plain Project) and stores destination rows
+ * [stripe_row0[g], stripe_row0[g+1]) at stripe_frames[g] + frame_index * rows_g * dw, i.e. as frame `frame_index`
+ * of the frame-major buffer of the stack job that owns stripe g (nl_stack_frames_dev).  Buffers of other GPUs are
+ * passed as their peer mappings (nl_ipc_open_handle): the exchange between the two shardings rides on the resample's
+ * stores.  The reference has no counterpart (one process: OpAlign fills f.Data, OpStack reads it, postprocess.go:142-191). */
+int  nl_project_scatter_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, int32_t dw, int32_t dh, const float trans[6],
+                            float oob, float multiplier, float offset, int32_t frame_index, void *const *stripe_frames,
+                            const int32_t *stripe_row0, int32_t n_stripes);
 
 /* ---- FITS pixel payload: replaces the conversion loops of internal/fits/read.go:176-443 (big-endian BITPIX
  * 8/16/32/64/-32/-64 -> fp32, v = float32(val)*Bscale + Bzero) and write.go:182-215 (fp32 -> big-endian,
@@ -219,6 +228,7 @@ int  nl_host_register(void *host, int64_t bytes);     /* page-lock an existing b
 int  nl_host_unregister(void *host);
 int  nl_memcpy_h2d(nl_ctx *ctx, void *dev, const void *host, int64_t bytes);   /* async on the stream */
 int  nl_memcpy_d2h(nl_ctx *ctx, void *host, const void *dev, int64_t bytes);   /* async on the stream */
+int  nl_memcpy_d2d(nl_ctx *ctx, void *dev_dst, const void *dev_src, int64_t bytes);   /* async on the stream */
 
 #ifdef __cplusplus
 }

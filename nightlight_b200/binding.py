@@ -77,6 +77,8 @@ DECLARED_SYMBOLS = {
     "nl_project_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float]),
     "nl_project_scaled": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float, C.c_float]),
     "nl_project_scaled_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float, C.c_float]),
+    "nl_project_scatter_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float, C.c_float,
+                                         C.c_int32, C.POINTER(_vp), _i32p, C.c_int32]),
     "nl_fits_decode": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float, _vp]),
     "nl_fits_decode_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.c_float, C.c_float, _vp]),
     "nl_fits_encode": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
@@ -98,6 +100,7 @@ DECLARED_SYMBOLS = {
     "nl_host_unregister": (C.c_int, [_vp]),
     "nl_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "nl_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    "nl_memcpy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
 }
 
 _lib = None

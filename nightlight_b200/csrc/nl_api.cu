@@ -214,4 +214,11 @@ int nl_memcpy_d2h(nl_ctx *ctx, void *host, const void *dev, int64_t bytes) {
     return NL_OK;
 }
 
+int nl_memcpy_d2d(nl_ctx *ctx, void *dev_dst, const void *dev_src, int64_t bytes) {
+    NL_REQUIRE(ctx && bytes >= 0, "bad argument");
+    CtxGuard g(ctx);
+    NL_CUDA(cudaMemcpyAsync(dev_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NL_OK;
+}
+
 }  // extern "C"

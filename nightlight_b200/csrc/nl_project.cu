@@ -58,6 +58,36 @@ __global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ 
         if (row0 + r < dh) __stcs(dst + (size_t)(row0 + r) * dw + col, v[r]);
 }
 
+// Frame-sharded resample feeding row-sharded stacking: the destination rows of one frame are not
+// stored into one image but straight into the stack jobs that own their row stripes -- the local job or, through
+// peer mappings over NVLink, the jobs of the other GPUs.  The frame-major -> stripe-major exchange between the two
+// shardings is thereby fused into the resample's stores: no staging image, no separate all-to-all pass.
+struct Scatter {
+    float *frame[NL_MAX_PEERS];       // where this frame's stripe g starts: job g's frame buffer + frame_index * stripe pixels
+    int row0[NL_MAX_PEERS + 1];       // stripe g owns destination rows [row0[g], row0[g+1])
+    int n;
+};
+
+template <bool SCALE>
+__global__ void __launch_bounds__(256) project_scatter_kernel(const float *__restrict__ src, int sw, int sh, Scatter sc, int dw, int dh,
+                                                              Affine inv, float oob, float mult, float offset) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
+    if (col >= dw || row0 >= dh) return;
+    float v[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, col, row0 + r, oob, mult, offset) : 0.0f;
+    int g = 0;
+    while (g + 1 < sc.n && row0 >= sc.row0[g + 1]) g++;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int row = row0 + r;
+        if (row >= dh) break;
+        while (g + 1 < sc.n && row >= sc.row0[g + 1]) g++;
+        sc.frame[g][(size_t)(row - sc.row0[g]) * dw + col] = v[r];
+    }
+}
+
 }  // namespace nl
 
 using namespace nl;
@@ -111,6 +141,42 @@ int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, fl
 int nl_project_scaled_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, float *dev_dst, int32_t dw, int32_t dh,
                           const float trans[6], float oob, float multiplier, float offset) {
     return project_launch(ctx, dev_src, sw, sh, dev_dst, dw, dh, trans, oob, true, multiplier, offset);
+}
+
+int nl_project_scatter_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, int32_t dw, int32_t dh, const float trans[6],
+                           float oob, float multiplier, float offset, int32_t frame_index, void *const *stripe_frames,
+                           const int32_t *stripe_row0, int32_t n_stripes) {
+    NL_REQUIRE(ctx && trans && stripe_frames && stripe_row0, "NULL argument");
+    NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0 && frame_index >= 0, "negative size or index");
+    NL_REQUIRE(n_stripes >= 1 && n_stripes <= NL_MAX_PEERS, "stripe count out of range");
+    NL_REQUIRE(stripe_row0[0] == 0 && stripe_row0[n_stripes] == dh, "stripes must cover rows [0, dh)");
+    float inv[6];
+    int rc = nl_transform_invert(trans, inv);
+    if (rc != NL_OK) return rc;
+    Scatter sc;
+    sc.n = n_stripes;
+    for (int g = 0; g < n_stripes; g++) {
+        const int rows = stripe_row0[g + 1] - stripe_row0[g];
+        NL_REQUIRE(rows >= 0, "stripe rows must ascend");
+        NL_REQUIRE(stripe_frames[g] || rows == 0, "NULL stripe buffer");
+        sc.row0[g] = stripe_row0[g];
+        sc.frame[g] = (float *)stripe_frames[g] + (size_t)frame_index * (size_t)rows * (size_t)dw;
+    }
+    sc.row0[n_stripes] = dh;
+    if (dw == 0 || dh == 0) return NL_OK;
+    NL_REQUIRE(dev_src || sw == 0 || sh == 0, "NULL image pointer");
+    CtxGuard g(ctx);
+    Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
+    dim3 block(64, 4);
+    dim3 grid((dw + block.x - 1) / block.x, (dh + 4 * block.y - 1) / (4 * block.y));
+    // multiplier 1 and offset 0 mean "no histogram match": d*1 + 0 would turn -0 into +0
+    if (multiplier == 1.0f && offset == 0.0f)
+        project_scatter_kernel<false><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, sc, dw, dh, a, oob, 1.0f, 0.0f);
+    else
+        project_scatter_kernel<true><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, sc, dw, dh, a, oob, multiplier, offset);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
 }
 
 static int project_host(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t sh, float *host_dst, int32_t dw, int32_t dh,

@@ -269,3 +269,42 @@ def test_find_stars_fuzz(ctx):
         assert len(got[0]) == len(want[0]), (it, len(got[0]), len(want[0]))
         assert got[0].tobytes() == want[0].tobytes(), it
         assert bits_equal([got[1], got[2]], [want[1], want[2]]), it
+
+
+def test_project_scatter_into_stripe_jobs(ctx):
+    """N4: the resample stores each destination row into the stack job that owns its row stripe (here three
+    ragged stripes on one device); every job then holds exactly its rows of every resampled frame"""
+    from nightlight_b200.stripes import all_stripes, scatter_project
+    from util import MODE_ID
+    rng = np.random.default_rng(77)
+    sw, sh, dw, dh, n = 150, 110, 131, 97, 5
+    stripes = all_stripes(dh, 3)
+    jobs = [nl.StackJob(ctx, n, rows * dw) for _, rows in stripes]
+    src_dev = ctx.dev_alloc(4 * sw * sh)
+    try:
+        frames, want = [], []
+        for k in range(n):
+            src = (rng.standard_normal(sw * sh) * 20 + 400).astype(np.float32)
+            th = np.deg2rad(rng.uniform(-3, 3))
+            trans = np.array([np.cos(th), -np.sin(th), rng.uniform(-6, 6), np.sin(th), np.cos(th), rng.uniform(-6, 6)], np.float32)
+            mult, off = (1.0, 0.0) if k % 2 == 0 else (1.0 + 0.01 * k, -3.0)
+            ctx.h2d(src_dev, src)
+            scatter_project(ctx, src_dev, sw, sh, dw, dh, trans, k, [j.frames_dev[0] for j in jobs],
+                            [s[0] for s in stripes] + [dh], float("nan"), mult, off)
+            ctx.sync()
+            want.append(nl.project(ctx, src, sw, sh, dw, dh, trans) if k % 2 == 0 else
+                        nl.project_scaled(ctx, src, sw, sh, dw, dh, trans, mult, off))
+        want = np.stack(want)
+        for (row0, rows), job in zip(stripes, jobs):
+            got = np.empty((n, rows * dw), np.float32)
+            ctx.d2h(got, job.frames_dev[0])
+            assert bits_equal(got, want[:, row0 * dw:(row0 + rows) * dw]), (row0, rows)
+        # and the stripes stack to the whole-image stack of the resampled frames
+        whole = O.stack(want, "median")
+        for (row0, rows), job in zip(stripes, jobs):
+            res = job.run(MODE_ID["median"])
+            assert bits_equal(res[0], whole[0][row0 * dw:(row0 + rows) * dw])
+    finally:
+        ctx.dev_free(src_dev)
+        for j in jobs:
+            j.close()

@@ -45,3 +45,44 @@ def test_two_rank_stripes_equal_whole():
     want, cl, ch = O.stack(O.synth_frames(n, 0, width * height), "sigma")
     assert np.array_equal(full.view(np.uint32), want.view(np.uint32))
     assert (tl, th) == (cl, ch)
+
+
+def _a2a_worker(rank, world, port, width, height, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nightlight_b200.stripes import alltoall_frames_to_stripes, frame_shard, stripe_rows
+    from oracle import oracle as O
+    ids = frame_shard(n, world, rank)
+    # "resampled" frames of this rank's frame shard: the synthetic frames themselves
+    local = torch.from_numpy(np.stack([O.synth_frame(0, width * height, k) for k in ids]))
+    mine = alltoall_frames_to_stripes(local, ids, n, width, height)
+    row0, rows = stripe_rows(height, world, rank)
+    res, cl, ch = O.stack(mine.numpy(), "sigma")
+    q.put((rank, row0, rows, res.copy(), cl, ch))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_frame_shards_to_row_stripes():
+    """N4 host logic: frames resampled frame-sharded (rank r owns frames r, r+G, ...) reach the row-sharded
+    stack through the all-to-all baseline; stripes stacked per rank equal the whole-image stack"""
+    from oracle import oracle as O
+    width, height, n, world = 29, 11, 9, 2            # ragged stripes (6 + 5 rows) and ragged frame shards (5 + 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_a2a_worker, args=(r, world, port, width, height, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want, cl, ch = O.stack(O.synth_frames(n, 0, width * height), "sigma")
+    full = np.empty(width * height, np.float32)
+    tl = th = 0
+    for rank, row0, rows, res, l, h in got:
+        full[row0 * width:(row0 + rows) * width] = res
+        tl, th = tl + l, th + h
+    assert np.array_equal(full.view(np.uint32), want.view(np.uint32))
+    assert (tl, th) == (cl, ch)
