@@ -682,53 +682,62 @@ NL_HD float reduce_linfit(float *g, int cur, int nmax, const float *ramp, float 
     sort_column<S>(g, cur, nmax);
     float mean = 0.0f;
     bool done = cur == 0;
+    // sum of the samples in index order: the first chain of MeanStdDev (stats.go:247-250).  After the first
+    // round it rides on the compaction of the survivors, which visits them in exactly that order.
+    float ysum = 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < cur; i++) ysum = nl_addf(ysum, g[i * S]);
     while (NL_ANY(!done)) {
         const int m = done ? 0 : cur;
         // LinearRegression(xs, ys), stats.go:569-586
         const float xm = ramp[2 * m], xsd = ramp[2 * m + 1];
-        // MeanStdDev(ys) (stats.go:246-261) with the covariance sum of LinearRegression (stats.go:575-579)
-        // riding on its second pass: three independent sequential chains, each in the reference's order
-        float ysum = 0.0f;
-#pragma unroll 8
-        for (int i = 0; i < m; i++) ysum = nl_addf(ysum, g[i * S]);
+        // the second pass of MeanStdDev(ys) (stats.go:251-259) with the covariance sum of LinearRegression
+        // (stats.go:575-579) riding on it: independent sequential chains, each in the reference's order
         const float fm = (float)m;
         const float ym = nl_divf(ysum, fm);
-        float yvar = 0.0f, corr = 0.0f;
+        float yvar = 0.0f, corr = 0.0f, fi = 0.0f;       // fi = float32(i), exact below 2^24
 #pragma unroll 8
         for (int i = 0; i < m; i++) {
             const float d = nl_subf(g[i * S], ym);
             yvar = nl_addf(yvar, nl_mulf(d, d));
-            corr = nl_addf(corr, nl_mulf(nl_subf((float)i, xm), d));
+            corr = nl_addf(corr, nl_mulf(nl_subf(fi, xm), d));
+            fi += 1.0f;
         }
         const float ysd = nl_sqrtf(nl_divf(yvar, fm));
-        corr = nl_divf(corr, nl_mulf(nl_mulf(xsd, ysd), nl_addf((float)m, 1.0f)));
+        corr = nl_divf(corr, nl_mulf(nl_mulf(xsd, ysd), nl_addf(fm, 1.0f)));
         const float slope = nl_divf(nl_mulf(corr, ysd), xsd);
         const float icpt = nl_subf(ym, nl_mulf(slope, xm));
         // mean absolute residual, stack.go:878-886
         float sigma = 0.0f;
+        fi = 0.0f;
 #pragma unroll 4
         for (int i = 0; i < m; i++) {
-            const float lin = nl_addf(nl_mulf((float)i, slope), icpt);
+            const float lin = nl_addf(nl_mulf(fi, slope), icpt);
             sigma = nl_addf(sigma, fabsf(nl_subf(g[i * S], lin)));
+            fi += 1.0f;
         }
-        sigma = nl_divf(sigma, (float)m);
-        // rejection (stack.go:889-909) fused with the compaction of the survivors
+        sigma = nl_divf(sigma, fm);
+        // rejection (stack.go:889-909) fused with the compaction of the survivors and their sum
         int w = 0;
         const float lob = nl_mulf(sig_lo, sigma), hib = nl_mulf(sig_hi, sigma);
+        float nsum = 0.0f;
+        fi = 0.0f;
 #pragma unroll 4
         for (int i = 0; i < m; i++) {
             const float v = g[i * S];
-            const float lin = nl_addf(nl_mulf((float)i, slope), icpt);
+            const float lin = nl_addf(nl_mulf(fi, slope), icpt);
+            fi += 1.0f;
             const bool low = nl_subf(lin, v) > lob;
             const bool high = !low && nl_subf(v, lin) > hib;
             ncl += low ? 1 : 0;
             nch += high ? 1 : 0;
-            if (!(low | high)) { g[w * S] = v; w++; }
+            if (!(low | high)) { g[w * S] = v; w++; nsum = nl_addf(nsum, v); }
         }
         if (!done) {
             mean = ym;
             if (w == cur || cur < 3) done = true;          // left == 0 || len < 3
             cur = w;
+            ysum = nsum;
         }
     }
     return mean;
