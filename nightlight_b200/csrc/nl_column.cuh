@@ -607,10 +607,16 @@ NL_HD void ramp_mean_stddev(int n, float &mean, float &sd) {
 // be 0 for a lane without samples, whose result is then meaningless.  A lane that has finished
 // keeps walking through the remaining passes of its neighbours with an empty column.
 template <int S, bool W, typename IDX>
-NL_HD float reduce_sigma(float *g, IDX *gw, const float *wtab, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
+NL_HD float reduce_sigma(float *g, IDX *gw, const float *wtab, int &cur, float sig_lo, float sig_hi, int &ncl, int &nch,
+                 int max_passes = 0, bool *pending = nullptr) {
+    // max_passes > 0: stop after that many clipping passes; *pending tells which columns are not finished.
+    // A column's state between passes is exactly (g[0..cur), gw[0..cur), cur): calling again resumes it.
     bool done = cur == 0;
     float result = 0.0f;
+    int pass = 0;
     while (NL_ANY(!done)) {
+        if (max_passes > 0 && pass == max_passes) break;
+        pass++;
         const int m = done ? 0 : cur;
         const float median = qselect_median<S, (S < 32)>(g, m);
         float mean, sd;
@@ -626,15 +632,22 @@ NL_HD float reduce_sigma(float *g, IDX *gw, const float *wtab, int cur, float si
             cur = left;
         }
     }
+    if (pending) *pending = !done;
     return result;
 }
 
 // stack.go:611-705 StackWinsorSigma / stack.go:710-829 StackWinsorSigmaWeighted
 template <int S, bool W, typename IDX>
-NL_HD float reduce_winsor(float *g, IDX *gw, const float *wtab, int cur, float sig_lo, float sig_hi, int &ncl, int &nch) {
+NL_HD float reduce_winsor(float *g, IDX *gw, const float *wtab, int &cur, float sig_lo, float sig_hi, int &ncl, int &nch,
+                 int max_passes = 0, bool *pending = nullptr) {
+    // max_passes > 0: stop after that many clipping passes; *pending tells which columns are not finished.
+    // A column's state between passes is exactly (g[0..cur), gw[0..cur), cur): calling again resumes it.
     bool done = cur == 0;
     float result = 0.0f;
+    int pass = 0;
     while (NL_ANY(!done)) {
+        if (max_passes > 0 && pass == max_passes) break;
+        pass++;
         const int m = done ? 0 : cur;
         const float median = qselect_median<S, (S < 32)>(g, m);
         float mean, sd;
@@ -651,6 +664,7 @@ NL_HD float reduce_winsor(float *g, IDX *gw, const float *wtab, int cur, float s
             cur = left;
         }
     }
+    if (pending) *pending = !done;
     return result;
 }
 

@@ -27,6 +27,20 @@ struct StackArgs {
     int n_peers;
     unsigned long long *clip;   // [2] low, high
     unsigned long long *tile_counter;   // next tile of the dynamic scheduler (zeroed per launch)
+    // Deferral of late clipping passes (sigma / winsorized sigma, 32-pixel tiles): most pixels settle after the same
+    // number of passes, a few need more, and a warp would walk all its 32 lanes through the passes of its slowest
+    // pixel.  Phase 0 therefore stops after `defer_passes` passes and moves the columns that are not finished --
+    // their state is exactly the permuted survivors and their count -- into a pool in global memory; phase 1 runs
+    // the same kernel over the pool, 32 unfinished columns to a warp.  The arithmetic of a column is unchanged.
+    int defer_passes;        // 0: never defer
+    int phase;               // 0: tiles of the frame stack, 1: tiles of the pool
+    float *pool;             // [cap/32][npad][32] sample columns
+    void *pool_idx;          // weighted modes: the frame-index columns, same layout
+    long long *pool_pixel;   // [cap] pixel of a slot
+    int *pool_cur;           // [cap] survivors of a slot
+    unsigned long long *pool_count;     // slots handed out (may exceed cap: the excess finished in place)
+    unsigned long long *pool_tile_counter;
+    long long pool_cap;      // slots, a multiple of 32
 };
 
 __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
@@ -92,7 +106,14 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
     IDX *gw = reinterpret_cast<IDX *>(region + (size_t)4 * (MODE == ST_MAD ? 2 : 1) * S * npad) + (lane % S);
     (void)sc; (void)gw;
 
-    const long long tiles = (a.pixels + S - 1) / S;
+    constexpr bool DEFER = S == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR);
+    const bool pool_phase = DEFER && a.phase == 1;
+    long long pool_slots = 0;
+    if (pool_phase) {
+        const unsigned long long c = *a.pool_count;
+        pool_slots = c < (unsigned long long)a.pool_cap ? (long long)c : a.pool_cap;
+    }
+    const long long tiles = pool_phase ? (pool_slots + 31) / 32 : (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
 
     // one mbarrier per warp for the TMA staging, in the last 64 bytes of the last gap (32-pixel tiles only:
@@ -108,17 +129,38 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
     }
 
     // dynamic tile scheduler: column work varies from pixel to pixel, so warps pull tiles from a counter
+    unsigned long long *const counter = pool_phase ? a.pool_tile_counter : a.tile_counter;
     auto next_tile = [&]() {
         unsigned long long v = 0;
-        if (lane == 0) v = atomicAdd(a.tile_counter, 1ull);
+        if (lane == 0) v = atomicAdd(counter, 1ull);
         return (long long)__shfl_sync(0xffffffffu, v, 0);
     };
     for (long long t = next_tile(); t < tiles; t = next_tile()) {
-        const long long p = t * S + lane;
-        const bool valid = lane < S && p < a.pixels;
+        long long p = t * S + lane;
+        bool valid = lane < S && p < a.pixels;
         int cur = 0;
         bool negzero = false;            // median mode: a -0.0 sample makes the SIGN of a zero median depend on the permutation
-        if (tma_tiles) {
+        if (pool_phase) {
+            // a tile of the pool: 32 deferred columns, laid out [sample][slot] like a slab
+            const long long slot = t * 32 + lane;
+            valid = slot < pool_slots;
+            p = valid ? a.pool_pixel[slot] : 0;
+            cur = valid ? a.pool_cur[slot] : 0;
+            const int rows = __reduce_max_sync(0xffffffffu, cur);
+            const float *src = a.pool + t * ((long long)npad * 32) + lane;
+            for (int i0 = 0; i0 < rows; i0 += 32) {               // 32 row segments of 128 bytes in flight per warp
+                float v[32];
+#pragma unroll
+                for (int u = 0; u < 32; u++) v[u] = ld_stream(src + (long long)(i0 + u) * 32);     // (npad is a multiple of 32)
+#pragma unroll
+                for (int u = 0; u < 32; u++) g[(i0 + u) * S] = v[u];
+            }
+            if (W) {
+                const IDX *srcw = reinterpret_cast<const IDX *>(a.pool_idx) + t * ((long long)npad * 32) + lane;
+#pragma unroll 8
+                for (int i = 0; i < rows; i++) gw[i * S] = srcw[(long long)i * 32];
+            }
+        } else if (tma_tiles) {
             // (the slab was last touched by this warp's generic-proxy loads and stores: order them
             // before the async-proxy writes of the tensor copies)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -168,6 +210,8 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         }
         if (cur == 0 && lane < S) g[0] = 0.0f;                    // parked lanes compare slot 0 with itself
         __syncwarp();
+        const int cur0 = cur;
+        bool spilled = false;
         float res;
         if (MODE == ST_MEDIAN) {
             // stack.go:274-303.  Only the value of the median matters -- except for the sign of a zero: with
@@ -175,16 +219,49 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
             // happens to leave at the median slot, so such (rare) tiles take the emulated quick-select.
             if (__any_sync(0xffffffffu, negzero)) res = qselect_median<S, (S < 32)>(g, cur);
             else res = median_by_value<S, (S < 32)>(g, cur);
-        } else if (MODE == ST_SIGMA) {
-            res = reduce_sigma<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
-        } else if (MODE == ST_WINSOR) {
-            res = reduce_winsor<S, W, IDX>(g, gw, a.weights, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else if (MODE == ST_SIGMA || MODE == ST_WINSOR) {
+            // (one call site in a loop: a second inlined copy of the reducer costs more in instruction fetch than the
+            // rare second round does)
+            int limit = (DEFER && !pool_phase) ? a.defer_passes : 0;
+            int c = cur;
+            bool mine = true;                       // this lane's column is still to be reduced here
+            res = 0.0f;
+            for (;;) {
+                bool pending = false;
+                float r;
+                if (MODE == ST_SIGMA) r = reduce_sigma<S, W, IDX>(g, gw, a.weights, c, a.sig_lo, a.sig_hi, ncl, nch, limit, &pending);
+                else r = reduce_winsor<S, W, IDX>(g, gw, a.weights, c, a.sig_lo, a.sig_hi, ncl, nch, limit, &pending);
+                if (mine) res = r;
+                const unsigned pm = limit > 0 ? __ballot_sync(0xffffffffu, pending) : 0u;
+                if (pm == 0u) break;
+                // hand the unfinished columns to the pool: consecutive slots for this warp's columns
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.pool_count, (unsigned long long)__popc(pm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const long long slot = (long long)base + __popc(pm & ((1u << lane) - 1u));
+                spilled = pending && slot < a.pool_cap;
+                if (spilled) {
+                    float *dst = a.pool + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
+                    for (int i = 0; i < c; i++) dst[(long long)i * 32] = g[i * S];
+                    if (W) {
+                        IDX *dstw = reinterpret_cast<IDX *>(a.pool_idx) + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
+                        for (int i = 0; i < c; i++) dstw[(long long)i * 32] = gw[i * S];
+                    }
+                    a.pool_pixel[slot] = p;
+                    a.pool_cur[slot] = c;
+                }
+                // a full pool: the columns that found no slot finish here in a second round, the other lanes parked
+                mine = pending && !spilled;
+                if (!__any_sync(0xffffffffu, mine)) break;
+                if (!mine) c = 0;
+                limit = 0;
+            }
         } else if (MODE == ST_MAD) {
             res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
         } else {
             res = reduce_linfit<S>(g, cur, __reduce_max_sync(0xffffffffu, cur), a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
         }
-        if (valid) store_result(a, p, cur == 0 ? a.ref_loc : res);   // stack.go:388-397
+        if (valid && !spilled) store_result(a, p, cur0 == 0 ? a.ref_loc : res);   // stack.go:388-397
         __syncwarp();
     }
     if (MODE >= ST_SIGMA) {
@@ -212,10 +289,15 @@ struct nl_stack_job {
     float *weights = nullptr;         // [n]
     float *ramp = nullptr;            // [2*(n+1)]
     bool ramp_ready = false;
-    unsigned long long *clip = nullptr;   // [3] device: clip low, clip high, tile counter
+    unsigned long long *clip = nullptr;   // [5] device: clip low, clip high, tile counter, pool slots handed out, pool tile counter
     unsigned long long *clip_host = nullptr;   // [2] pinned
     alignas(64) CUtensorMap tmap;     // [n][pixels] fp32, box 32 frames x 32 pixels, NaN fill
     bool tmap_ok = false;
+    // pool of deferred columns (StackArgs): one allocation, carved into samples | indices | pixel | cur
+    void *pool = nullptr;
+    long long pool_cap = 0;           // slots
+    int pool_idx_bytes = 0;           // bytes per index element the pool was sized for (0: none)
+    bool pool_failed = false;         // allocation failed once: run without deferral
 };
 
 namespace nl {
@@ -239,12 +321,52 @@ inline int launch_column(nl_stack_job *job, const StackArgs &args) {
     const long long tiles = (job->pixels + S - 1) / S;
     long long grid = (long long)ctx->sm_count * ctas_per_sm;
     const long long need = (tiles + warps - 1) / warps;
-    if (grid > need) grid = need;
+    if (grid > need && args.phase == 0) grid = need;       // (the pool's tile count is only known on the device)
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, warps * 32, smem, ctx->stream>>>(args, job->tmap);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;
+}
+
+// After how many clipping passes unfinished columns move to the pool.  Sigma clipping of N ~ 256 samples settles
+// after three passes for four pixels in five and after four for nearly all others (profiles/r01_summary.md);
+// measured on the synthetic workload, 512-row stripe: sigma 7.5 -> 6.9 ms at 3, winsorized 11.8 -> 10.7 ms at 2.
+inline int defer_passes_for(int mode) {
+    if (const char *e = getenv("NL_DEFER_PASSES")) return atoi(e);       // development override (A/B measurements)
+    return mode == ST_SIGMA ? 3 : 2;       // winsorized clipping settles one pass earlier
+}
+
+// The pool holds up to a quarter of the job's pixels (columns that find no slot finish in place).
+inline bool ensure_pool(nl_stack_job *job, int idx_bytes, StackArgs *a) {
+    if (job->pool_failed) return false;
+    const long long npad = (job->n + 31) & ~31;
+    const size_t per_slot = (size_t)npad * (4 + (size_t)idx_bytes) + sizeof(long long) + sizeof(int);
+    if (!job->pool || job->pool_idx_bytes < idx_bytes) {
+        if (job->pool) { cudaStreamSynchronize(job->ctx->stream); cudaFree(job->pool); job->pool = nullptr; }
+        long long cap = ((job->pixels / 4) + 31) & ~31ll;
+        if (cap < 32) cap = 32;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); job->pool_failed = true; return false; }
+        const long long fit = (long long)(free_b / 2 / per_slot) & ~31ll;
+        if (cap > fit) cap = fit;
+        if (cap < 32 || cudaMalloc(&job->pool, (size_t)cap * per_slot + 256) != cudaSuccess) {
+            cudaGetLastError();
+            job->pool = nullptr;
+            job->pool_failed = true;
+            return false;
+        }
+        job->pool_cap = cap;
+        job->pool_idx_bytes = idx_bytes;
+    }
+    char *base = (char *)job->pool;
+    const size_t cap = (size_t)job->pool_cap;
+    a->pool = (float *)base;
+    a->pool_pixel = (long long *)(base + cap * (size_t)npad * 4);
+    a->pool_cur = (int *)(base + cap * (size_t)npad * 4 + cap * sizeof(long long));
+    a->pool_idx = base + cap * (size_t)npad * 4 + cap * (sizeof(long long) + sizeof(int));
+    a->pool_cap = job->pool_cap;
+    return true;
 }
 
 template <int MODE, bool W, typename IDX>
@@ -271,6 +393,17 @@ inline int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     if (const char *force = getenv("NL_TILE_WIDTH")) {             // development override (A/B measurements)
         const int wdt = atoi(force);
         if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + 2 * gap) * wdt <= cap) best = wdt;
+    }
+    if (best == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR)) {
+        // deferral of late clipping passes (see StackArgs): phase 0 over the frame stack, phase 1 over the pool
+        StackArgs a2 = args;
+        a2.defer_passes = defer_passes_for(MODE);
+        if (a2.defer_passes > 0 && ensure_pool(job, W ? (int)sizeof(IDX) : 0, &a2)) {
+            int rc = launch_column<MODE, W, 32, IDX>(job, a2);
+            if (rc != NL_OK) return rc;
+            a2.phase = 1;
+            return launch_column<MODE, W, 32, IDX>(job, a2);
+        }
     }
     switch (best) {
     case 32: return launch_column<MODE, W, 32, IDX>(job, args);
