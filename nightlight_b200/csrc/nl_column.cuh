@@ -692,8 +692,11 @@ NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi,
 // slots removed -- a stable compaction, no second sort.  All 32 lanes call this together (nmax = the
 // longest column of the warp); cur may be 0.
 template <int S>
-NL_HD float reduce_linfit(float *g, int cur, int nmax, const float *ramp, float sig_lo, float sig_hi, int &ncl, int &nch) {
-    sort_column<S>(g, cur, nmax);
+NL_HD float reduce_linfit(float *g, int &cur, int nmax, const float *ramp, float sig_lo, float sig_hi, int &ncl, int &nch,
+                          bool sorted = false, int max_iters = 0, bool *pending = nullptr) {
+    // max_iters > 0: stop after that many rejection rounds; *pending tells which columns are not finished.  A column's
+    // state between rounds is its sorted survivors g[0..cur): calling again with sorted = true resumes it.
+    if (!sorted) sort_column<S>(g, cur, nmax);
     float mean = 0.0f;
     bool done = cur == 0;
     // sum of the samples in index order: the first chain of MeanStdDev (stats.go:247-250).  After the first
@@ -701,7 +704,10 @@ NL_HD float reduce_linfit(float *g, int cur, int nmax, const float *ramp, float 
     float ysum = 0.0f;
 #pragma unroll 8
     for (int i = 0; i < cur; i++) ysum = nl_addf(ysum, g[i * S]);
+    int round = 0;
     while (NL_ANY(!done)) {
+        if (max_iters > 0 && round == max_iters) break;
+        round++;
         const int m = done ? 0 : cur;
         // LinearRegression(xs, ys), stats.go:569-586
         const float xm = ramp[2 * m], xsd = ramp[2 * m + 1];
@@ -754,6 +760,7 @@ NL_HD float reduce_linfit(float *g, int cur, int nmax, const float *ramp, float 
             ysum = nsum;
         }
     }
+    if (pending) *pending = !done;
     return mean;
 }
 

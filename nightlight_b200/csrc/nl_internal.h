@@ -10,6 +10,7 @@
 #include "../../include/nightlight_cuda.h"
 
 #define NL_MAX_PEERS 8
+#define NL_JOB_COUNTERS 32     // device counters of a stack job: clip low/high, tile counter, two per deferral round
 
 struct nl_ctx {
     int device = 0;

@@ -132,7 +132,7 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     const bool weighted = host_weights != nullptr;
     if (mode == NL_ST_MAD_SIGMA && weighted)
         return set_error(NL_E_UNSUPPORTED, "MADSigma stacking with weights is still unimplemented");         // stack.go:185
-    NL_CUDA(cudaMemsetAsync(job->clip, 0, 5 * sizeof(unsigned long long), ctx->stream));
+    NL_CUDA(cudaMemsetAsync(job->clip, 0, NL_JOB_COUNTERS * sizeof(unsigned long long), ctx->stream));
     if (job->pixels == 0) return NL_OK;
     if (weighted)
         NL_CUDA(cudaMemcpyAsync(job->weights, host_weights, sizeof(float) * job->n, cudaMemcpyHostToDevice, ctx->stream));
@@ -148,8 +148,8 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     a.frames = job->frames; a.stride = job->pixels; a.pixels = job->pixels; a.n = job->n;
     a.weights = weighted ? job->weights : nullptr; a.ramp = job->ramp;
     a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip; a.tile_counter = job->clip + 2;
-    a.defer_passes = 0; a.phase = 0; a.pool = nullptr; a.pool_idx = nullptr; a.pool_pixel = nullptr; a.pool_cur = nullptr;
-    a.pool_count = job->clip + 3; a.pool_tile_counter = job->clip + 4; a.pool_cap = 0;
+    a.defer_passes = 0; a.phase = 0; a.pool_in = StackArgs::Pool{nullptr, nullptr, nullptr, nullptr, job->clip + 3, 0};
+    a.pool_out = a.pool_in; a.pool_tile_counter = job->clip + 4;
     a.n_peers = n_peers;
     for (int e = 0; e < NL_MAX_PEERS; e++) a.peer_out[e] = e < n_peers ? peer_outs[e] : nullptr;
     switch (mode) {
@@ -210,7 +210,7 @@ int nl_stack_begin(nl_ctx *ctx, int32_t n_frames, int64_t pixels, nl_stack_job *
     if (e == cudaSuccess) e = cudaMalloc(&j->out, sizeof(float) * (size_t)(pixels > 0 ? pixels : 1));
     if (e == cudaSuccess) e = cudaMalloc(&j->weights, sizeof(float) * (size_t)n_frames);
     if (e == cudaSuccess) e = cudaMalloc(&j->ramp, sizeof(float) * 2 * ((size_t)n_frames + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&j->clip, 5 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&j->clip, NL_JOB_COUNTERS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&j->clip_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         nl_stack_end(j);

@@ -27,21 +27,25 @@ struct StackArgs {
     int n_peers;
     unsigned long long *clip;   // [2] low, high
     unsigned long long *tile_counter;   // next tile of the dynamic scheduler (zeroed per launch)
-    // Deferral of late clipping passes (sigma / winsorized sigma, 32-pixel tiles): most pixels settle after the same
-    // number of passes, a few need more, and a warp would walk all its 32 lanes through the passes of its slowest
-    // pixel.  Phase 0 therefore stops after `defer_passes` passes and moves the columns that are not finished --
-    // their state is exactly the permuted survivors and their count -- into a pool in global memory; phase 1 runs
-    // the same kernel over the pool, 32 unfinished columns to a warp.  The arithmetic of a column is unchanged.
-    int defer_passes;        // 0: never defer
-    int phase;               // 0: tiles of the frame stack, 1: tiles of the pool
-    float *pool;             // [cap/32][npad][32] sample columns
-    void *pool_idx;          // weighted modes: the frame-index columns, same layout
-    long long *pool_pixel;   // [cap] pixel of a slot
-    int *pool_cur;           // [cap] survivors of a slot
-    unsigned long long *pool_count;     // slots handed out (may exceed cap: the excess finished in place)
-    unsigned long long *pool_tile_counter;
-    long long pool_cap;      // slots, a multiple of 32
+    // Deferral of late passes (sigma / winsorized sigma / linear fit, 32-pixel tiles): pixels need different
+    // numbers of clipping passes (rejection rounds), and a warp would walk all its 32 lanes through the passes of
+    // its slowest pixel.  A launch therefore stops after `defer_passes` passes and moves the columns that are not
+    // finished -- their state is exactly the (permuted or sorted) survivors and their count -- into a pool in
+    // global memory; the next launch runs the same kernel over that pool, 32 unfinished columns to a warp, and may
+    // defer again into a second pool.  The arithmetic of a column is unchanged.
+    int defer_passes;        // 0: run every column to the end
+    int phase;               // 0: tiles of the frame stack; >= 1: tiles of the input pool
+    struct Pool {
+        float *samples;      // [cap/32][npad][32] sample columns
+        void *idx;           // weighted modes: the frame-index columns, same layout
+        long long *pixel;    // [cap] pixel of a slot
+        int *cur;            // [cap] survivors of a slot
+        unsigned long long *count;     // slots handed out (may exceed cap: the excess finished in place)
+        long long cap;       // slots, a multiple of 32
+    } pool_in, pool_out;
+    unsigned long long *pool_tile_counter;   // scheduler of the input pool's tiles
 };
+
 
 __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 
@@ -106,12 +110,12 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
     IDX *gw = reinterpret_cast<IDX *>(region + (size_t)4 * (MODE == ST_MAD ? 2 : 1) * S * npad) + (lane % S);
     (void)sc; (void)gw;
 
-    constexpr bool DEFER = S == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR);
-    const bool pool_phase = DEFER && a.phase == 1;
+    constexpr bool DEFER = S == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT);
+    const bool pool_phase = DEFER && a.phase >= 1;
     long long pool_slots = 0;
     if (pool_phase) {
-        const unsigned long long c = *a.pool_count;
-        pool_slots = c < (unsigned long long)a.pool_cap ? (long long)c : a.pool_cap;
+        const unsigned long long c = *a.pool_in.count;
+        pool_slots = c < (unsigned long long)a.pool_in.cap ? (long long)c : a.pool_in.cap;
     }
     const long long tiles = pool_phase ? (pool_slots + 31) / 32 : (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
@@ -144,10 +148,10 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
             // a tile of the pool: 32 deferred columns, laid out [sample][slot] like a slab
             const long long slot = t * 32 + lane;
             valid = slot < pool_slots;
-            p = valid ? a.pool_pixel[slot] : 0;
-            cur = valid ? a.pool_cur[slot] : 0;
+            p = valid ? a.pool_in.pixel[slot] : 0;
+            cur = valid ? a.pool_in.cur[slot] : 0;
             const int rows = __reduce_max_sync(0xffffffffu, cur);
-            const float *src = a.pool + t * ((long long)npad * 32) + lane;
+            const float *src = a.pool_in.samples + t * ((long long)npad * 32) + lane;
             for (int i0 = 0; i0 < rows; i0 += 32) {               // 32 row segments of 128 bytes in flight per warp
                 float v[32];
 #pragma unroll
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
                 for (int u = 0; u < 32; u++) g[(i0 + u) * S] = v[u];
             }
             if (W) {
-                const IDX *srcw = reinterpret_cast<const IDX *>(a.pool_idx) + t * ((long long)npad * 32) + lane;
+                const IDX *srcw = reinterpret_cast<const IDX *>(a.pool_in.idx) + t * ((long long)npad * 32) + lane;
 #pragma unroll 8
                 for (int i = 0; i < rows; i++) gw[i * S] = srcw[(long long)i * 32];
             }
@@ -219,47 +223,48 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
             // happens to leave at the median slot, so such (rare) tiles take the emulated quick-select.
             if (__any_sync(0xffffffffu, negzero)) res = qselect_median<S, (S < 32)>(g, cur);
             else res = median_by_value<S, (S < 32)>(g, cur);
-        } else if (MODE == ST_SIGMA || MODE == ST_WINSOR) {
-            // (one call site in a loop: a second inlined copy of the reducer costs more in instruction fetch than the
-            // rare second round does)
-            int limit = (DEFER && !pool_phase) ? a.defer_passes : 0;
+        } else if (MODE == ST_MAD) {
+            res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
+        } else {
+            // sigma, winsorized sigma, linear fit.  (One call site in a loop: a second inlined copy of the reducer
+            // costs more in instruction fetch than the rare second round does.)
+            int limit = DEFER ? a.defer_passes : 0;
             int c = cur;
             bool mine = true;                       // this lane's column is still to be reduced here
+            bool sorted = pool_phase;               // linear fit: pooled columns are sorted already
             res = 0.0f;
             for (;;) {
                 bool pending = false;
                 float r;
                 if (MODE == ST_SIGMA) r = reduce_sigma<S, W, IDX>(g, gw, a.weights, c, a.sig_lo, a.sig_hi, ncl, nch, limit, &pending);
-                else r = reduce_winsor<S, W, IDX>(g, gw, a.weights, c, a.sig_lo, a.sig_hi, ncl, nch, limit, &pending);
+                else if (MODE == ST_WINSOR) r = reduce_winsor<S, W, IDX>(g, gw, a.weights, c, a.sig_lo, a.sig_hi, ncl, nch, limit, &pending);
+                else r = reduce_linfit<S>(g, c, __reduce_max_sync(0xffffffffu, c), a.ramp, a.sig_lo, a.sig_hi, ncl, nch, sorted, limit, &pending);
                 if (mine) res = r;
                 const unsigned pm = limit > 0 ? __ballot_sync(0xffffffffu, pending) : 0u;
                 if (pm == 0u) break;
                 // hand the unfinished columns to the pool: consecutive slots for this warp's columns
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.pool_count, (unsigned long long)__popc(pm));
+                if (lane == 0) base = atomicAdd(a.pool_out.count, (unsigned long long)__popc(pm));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 const long long slot = (long long)base + __popc(pm & ((1u << lane) - 1u));
-                spilled = pending && slot < a.pool_cap;
+                spilled = pending && slot < a.pool_out.cap;
                 if (spilled) {
-                    float *dst = a.pool + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
+                    float *dst = a.pool_out.samples + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
                     for (int i = 0; i < c; i++) dst[(long long)i * 32] = g[i * S];
                     if (W) {
-                        IDX *dstw = reinterpret_cast<IDX *>(a.pool_idx) + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
+                        IDX *dstw = reinterpret_cast<IDX *>(a.pool_out.idx) + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
                         for (int i = 0; i < c; i++) dstw[(long long)i * 32] = gw[i * S];
                     }
-                    a.pool_pixel[slot] = p;
-                    a.pool_cur[slot] = c;
+                    a.pool_out.pixel[slot] = p;
+                    a.pool_out.cur[slot] = c;
                 }
                 // a full pool: the columns that found no slot finish here in a second round, the other lanes parked
                 mine = pending && !spilled;
                 if (!__any_sync(0xffffffffu, mine)) break;
                 if (!mine) c = 0;
                 limit = 0;
+                sorted = true;
             }
-        } else if (MODE == ST_MAD) {
-            res = reduce_mad<S>(g, sc, cur, a.sig_lo, a.sig_hi, ncl, nch);
-        } else {
-            res = reduce_linfit<S>(g, cur, __reduce_max_sync(0xffffffffu, cur), a.ramp, a.sig_lo, a.sig_hi, ncl, nch);
         }
         if (valid && !spilled) store_result(a, p, cur0 == 0 ? a.ref_loc : res);   // stack.go:388-397
         __syncwarp();
@@ -289,14 +294,15 @@ struct nl_stack_job {
     float *weights = nullptr;         // [n]
     float *ramp = nullptr;            // [2*(n+1)]
     bool ramp_ready = false;
-    unsigned long long *clip = nullptr;   // [5] device: clip low, clip high, tile counter, pool slots handed out, pool tile counter
+    unsigned long long *clip = nullptr;   // [NL_JOB_COUNTERS] device: clip low, clip high, tile counter, then per deferral round
+                                          // the slots it handed out and the tile counter of the round that consumes them
     unsigned long long *clip_host = nullptr;   // [2] pinned
     alignas(64) CUtensorMap tmap;     // [n][pixels] fp32, box 32 frames x 32 pixels, NaN fill
     bool tmap_ok = false;
-    // pool of deferred columns (StackArgs): one allocation, carved into samples | indices | pixel | cur
+    // the two pools of deferred columns (StackArgs): one allocation, each carved into samples | pixel | cur | indices
     void *pool = nullptr;
-    long long pool_cap = 0;           // slots
-    int pool_idx_bytes = 0;           // bytes per index element the pool was sized for (0: none)
+    long long pool_cap[2] = {0, 0};   // slots
+    int pool_idx_bytes = 0;           // bytes per index element the pools were sized for (0: none)
     bool pool_failed = false;         // allocation failed once: run without deferral
 };
 
@@ -329,43 +335,74 @@ inline int launch_column(nl_stack_job *job, const StackArgs &args) {
     return NL_OK;
 }
 
-// After how many clipping passes unfinished columns move to the pool.  Sigma clipping of N ~ 256 samples settles
-// after three passes for four pixels in five and after four for nearly all others (profiles/r01_summary.md);
-// measured on the synthetic workload, 512-row stripe: sigma 7.5 -> 6.9 ms at 3, winsorized 11.8 -> 10.7 ms at 2.
-inline int defer_passes_for(int mode) {
-    if (const char *e = getenv("NL_DEFER_PASSES")) return atoi(e);       // development override (A/B measurements)
-    return mode == ST_SIGMA ? 3 : 2;       // winsorized clipping settles one pass earlier
+// Deferral schedule: after how many passes (cumulative) each launch hands its unfinished columns on; the launch
+// after the last entry runs to the end.  Measured on the synthetic workload (512-row stripe of 256 frames):
+//   sigma clipping settles after three passes for four pixels in five and after four for nearly all others:
+//     7.5 -> 6.9 ms with {3};  winsorized clipping settles one pass earlier: 11.8 -> 10.7 ms with {2};
+//   the linear fit needs 4 .. 40 rejection rounds per pixel (mean 12, slowest of 32 pixels: 26.6), so its columns
+//     are regrouped several times.
+// NL_DEFER_PASSES (development override, A/B measurements): a comma list, "0" switches the deferral off.
+struct DeferSchedule { int n; int at[8]; double frac[2]; };
+inline DeferSchedule defer_schedule(int mode) {
+    DeferSchedule d{0, {0}, {0.25, 0.0}};
+    if (mode == ST_SIGMA) { d.n = 1; d.at[0] = 3; }
+    else if (mode == ST_WINSOR) { d.n = 1; d.at[0] = 2; }
+    else if (mode == ST_LINFIT) { d.n = 6; const int at[6] = {8, 12, 16, 20, 24, 30}; for (int i = 0; i < 6; i++) d.at[i] = at[i]; d.frac[0] = 0.75; d.frac[1] = 0.5; }
+    if (const char *e = getenv("NL_DEFER_PASSES")) {
+        d.n = 0;
+        for (const char *q = e; *q && d.n < 8;) {
+            const int v = atoi(q);
+            if (v > (d.n ? d.at[d.n - 1] : 0)) d.at[d.n++] = v;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        if (d.n > 1) { d.frac[0] = 1.0; d.frac[1] = 1.0; } else if (d.n == 1) { d.frac[0] = d.at[0] < 3 ? 1.0 : 0.25; }
+    }
+    return d;
 }
 
-// The pool holds up to a quarter of the job's pixels (columns that find no slot finish in place).
-inline bool ensure_pool(nl_stack_job *job, int idx_bytes, StackArgs *a) {
+// Two pools (a launch reads one and fills the other); pool k holds up to frac[k] of the job's pixels, columns that
+// find no slot finish in place.  false: no memory for them, run without deferral.
+inline bool ensure_pools(nl_stack_job *job, int idx_bytes, const double frac[2], StackArgs::Pool pools[2]) {
     if (job->pool_failed) return false;
     const long long npad = (job->n + 31) & ~31;
     const size_t per_slot = (size_t)npad * (4 + (size_t)idx_bytes) + sizeof(long long) + sizeof(int);
-    if (!job->pool || job->pool_idx_bytes < idx_bytes) {
+    long long want[2];
+    for (int k = 0; k < 2; k++) {
+        want[k] = frac[k] > 0.0 ? (((long long)((double)job->pixels * frac[k]) + 31) & ~31ll) : 0;
+        if (frac[k] > 0.0 && want[k] < 32) want[k] = 32;
+    }
+    if (!job->pool || job->pool_idx_bytes < idx_bytes || job->pool_cap[0] < want[0] || job->pool_cap[1] < want[1]) {
         if (job->pool) { cudaStreamSynchronize(job->ctx->stream); cudaFree(job->pool); job->pool = nullptr; }
-        long long cap = ((job->pixels / 4) + 31) & ~31ll;
-        if (cap < 32) cap = 32;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); job->pool_failed = true; return false; }
-        const long long fit = (long long)(free_b / 2 / per_slot) & ~31ll;
-        if (cap > fit) cap = fit;
-        if (cap < 32 || cudaMalloc(&job->pool, (size_t)cap * per_slot + 256) != cudaSuccess) {
+        // never take more than half of what is free; shrink both pools alike
+        const double need = (double)(want[0] + want[1]) * (double)per_slot;
+        if (need > 0.5 * (double)free_b) {
+            const double f = 0.5 * (double)free_b / need;
+            for (int k = 0; k < 2; k++) want[k] = (long long)((double)want[k] * f) & ~31ll;
+        }
+        if (want[0] < 32 || cudaMalloc(&job->pool, (size_t)(want[0] + want[1]) * per_slot + 512) != cudaSuccess) {
             cudaGetLastError();
             job->pool = nullptr;
             job->pool_failed = true;
             return false;
         }
-        job->pool_cap = cap;
+        job->pool_cap[0] = want[0];
+        job->pool_cap[1] = want[1];
         job->pool_idx_bytes = idx_bytes;
     }
     char *base = (char *)job->pool;
-    const size_t cap = (size_t)job->pool_cap;
-    a->pool = (float *)base;
-    a->pool_pixel = (long long *)(base + cap * (size_t)npad * 4);
-    a->pool_cur = (int *)(base + cap * (size_t)npad * 4 + cap * sizeof(long long));
-    a->pool_idx = base + cap * (size_t)npad * 4 + cap * (sizeof(long long) + sizeof(int));
-    a->pool_cap = job->pool_cap;
+    for (int k = 0; k < 2; k++) {
+        const size_t cap = (size_t)job->pool_cap[k];
+        pools[k].samples = (float *)base;
+        pools[k].pixel = (long long *)(base + cap * (size_t)npad * 4);
+        pools[k].cur = (int *)(base + cap * (size_t)npad * 4 + cap * sizeof(long long));
+        pools[k].idx = base + cap * (size_t)npad * 4 + cap * (sizeof(long long) + sizeof(int));
+        pools[k].cap = job->pool_cap[k];
+        pools[k].count = nullptr;
+        base += (cap * per_slot + 255) & ~(size_t)255;
+    }
     return true;
 }
 
@@ -394,15 +431,25 @@ inline int launch_column_i(nl_stack_job *job, const StackArgs &args) {
         const int wdt = atoi(force);
         if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + 2 * gap) * wdt <= cap) best = wdt;
     }
-    if (best == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR)) {
-        // deferral of late clipping passes (see StackArgs): phase 0 over the frame stack, phase 1 over the pool
-        StackArgs a2 = args;
-        a2.defer_passes = defer_passes_for(MODE);
-        if (a2.defer_passes > 0 && ensure_pool(job, W ? (int)sizeof(IDX) : 0, &a2)) {
-            int rc = launch_column<MODE, W, 32, IDX>(job, a2);
-            if (rc != NL_OK) return rc;
-            a2.phase = 1;
-            return launch_column<MODE, W, 32, IDX>(job, a2);
+    if (best == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT)) {
+        // deferral of late passes (see StackArgs): launch 0 over the frame stack, then one launch per pool generation
+        const DeferSchedule d = defer_schedule(MODE);
+        StackArgs::Pool pools[2];
+        if (d.n > 0 && ensure_pools(job, W ? (int)sizeof(IDX) : 0, d.frac, pools)) {
+            StackArgs a2 = args;
+            const int rounds = pools[1].cap >= 32 ? d.n : 1;          // without a second pool: defer once
+            for (int r = 0; r <= rounds; r++) {
+                a2.phase = r;
+                a2.defer_passes = r < rounds ? d.at[r] - (r ? d.at[r - 1] : 0) : 0;
+                a2.pool_in = pools[(r + 1) & 1];                      // what launch r-1 filled
+                a2.pool_in.count = job->clip + 3 + 2 * (r > 0 ? r - 1 : 0);
+                a2.pool_tile_counter = job->clip + 4 + 2 * (r > 0 ? r - 1 : 0);
+                a2.pool_out = pools[r & 1];
+                a2.pool_out.count = job->clip + 3 + 2 * r;
+                int rc = launch_column<MODE, W, 32, IDX>(job, a2);
+                if (rc != NL_OK) return rc;
+            }
+            return NL_OK;
         }
     }
     switch (best) {

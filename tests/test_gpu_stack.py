@@ -311,14 +311,14 @@ def test_random_shapes_and_modes_fuzz(ctx, seed):
         check_against_oracle(ctx, frames, mode, weighted, sl, sh, ref_loc=float(rng.choice([0.0, 7.5])), w=w)
 
 
-@pytest.mark.parametrize("defer", ["1", "2", "3", "0"])
-@pytest.mark.parametrize("mode,weighted", [("sigma", False), ("sigma", True), ("winsor", False), ("winsor", True)])
+@pytest.mark.parametrize("defer", ["1", "2", "3", "0", "1,2,4", "2,3,5,8,13"])
+@pytest.mark.parametrize("mode,weighted", [("sigma", False), ("sigma", True), ("winsor", False), ("winsor", True), ("linfit", False)])
 def test_deferred_clipping_passes_pool_and_overflow(ctx, monkeypatch, mode, weighted, defer):
     """Late clipping passes are deferred to a pool of unfinished columns and finished by a second launch; the pool
     holds a quarter of the pixels, the overflow finishes in place.  Heavy-tailed samples make most pixels need
     many passes, so with an early limit the pool overflows; every variant must equal the oracle bit for bit."""
     monkeypatch.setenv("NL_DEFER_PASSES", defer)
-    rng = np.random.default_rng(int(defer) * 7 + len(mode) + weighted)
+    rng = np.random.default_rng(len(defer) * 7 + len(mode) + weighted)
     n, p = 96, 32 * 61 + 5                              # 32-pixel tiles and a ragged last tile
     frames = (rng.standard_t(2.0, size=(n, p)) * 25 + 500).astype(np.float32)
     frames[rng.random((n, p)) < 0.01] = np.nan
@@ -326,3 +326,10 @@ def test_deferred_clipping_passes_pool_and_overflow(ctx, monkeypatch, mode, weig
     frames[1:, 11] = np.nan                             # a single sample
     check_against_oracle(ctx, frames, mode, weighted, 2.0, 2.5, ref_loc=123.0)
     check_against_oracle(ctx, frames[:40], mode, weighted)
+
+
+def test_default_deferral_schedules_on_the_synthetic_workload(ctx):
+    """the schedules the library uses by default (sigma {3}, winsor {2}, linear fit {8,...,30}), on generator data"""
+    frames = O.synth_frames(128, 4096 * 100, 32 * 300)
+    for mode, weighted in (("sigma", False), ("winsor", True), ("linfit", False)):
+        check_against_oracle(ctx, frames, mode, weighted)
