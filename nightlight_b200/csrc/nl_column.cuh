@@ -529,41 +529,88 @@ NL_HD void sort_stage(float *a, int n) {
         }
     }
 }
+// Register blocking: the comparators of every stage with distance <= 8 stay inside an aligned block of 16
+// consecutive samples, so a lane loads a block into registers (positions >= n as +inf), runs those stages there
+// (two FMNMX per comparator, no shared-memory traffic, no guards) and stores the block back.
+template <int SS> NL_HD void reg_clean(float (&v)[16]) {          // half-cleaner of distance SS
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int lo = ((i & ~(SS - 1)) << 1) | (i & (SS - 1)), hi = lo | SS;
+        const float x = v[lo], y = v[hi];
+        v[lo] = fminf(x, y); v[hi] = fmaxf(x, y);
+    }
+}
+template <int K> NL_HD void reg_mirror(float (&v)[16]) {          // first stage of the merge of sorted K/2-runs
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int lo = ((i & ~((K >> 1) - 1)) << 1) | (i & ((K >> 1) - 1)), hi = lo ^ (K - 1);
+        const float x = v[lo], y = v[hi];
+        v[lo] = fminf(x, y); v[hi] = fmaxf(x, y);
+    }
+}
+// FULL: sort every block of 16 (merges 2, 4, 8, 16); else: the last four stages (distance 8, 4, 2, 1) of a wider merge
+template <int S, bool FULL>
+NL_HD void sort_blocks16(float *a, int n, int nmax) {
+    for (int b = 0; b < nmax; b += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = b + j < n ? a[(b + j) * S] : INFINITY;
+        if (FULL) {
+            reg_mirror<2>(v);
+            reg_mirror<4>(v); reg_clean<1>(v);
+            reg_mirror<8>(v); reg_clean<2>(v); reg_clean<1>(v);
+            reg_mirror<16>(v); reg_clean<4>(v); reg_clean<2>(v); reg_clean<1>(v);
+        } else {
+            reg_clean<8>(v); reg_clean<4>(v); reg_clean<2>(v); reg_clean<1>(v);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (b + j < n) a[(b + j) * S] = v[j];
+    }
+}
+// stages of merge K with distance SS .. 16 in shared memory
 template <int S, int K, int SS, int P>
-struct SortStages {
+struct WideStages {
     static NL_HD void run(float *a, int n) {
         sort_stage<S, K, SS, P>(a, n);
-        SortStages<S, K, (SS >> 1), P>::run(a, n);
+        WideStages<S, K, (SS >> 1), P>::run(a, n);
     }
 };
 template <int S, int K, int P>
-struct SortStages<S, K, 0, P> {
+struct WideStages<S, K, 8, P> {
     static NL_HD void run(float *, int) {}
 };
-template <int S, int K, int P>
-struct SortMerges {
-    static NL_HD void run(float *a, int n) {
-        SortMerges<S, (K >> 1), P>::run(a, n);
-        SortStages<S, K, (K >> 1), P>::run(a, n);
+template <int S, int K, int P, bool LIVE = (K <= P)>
+struct MergeUp {
+    static NL_HD void run(float *a, int n, int nmax) {
+        WideStages<S, K, (K >> 1), P>::run(a, n);
+        sort_blocks16<S, false>(a, n, nmax);
+        MergeUp<S, (K << 1), P>::run(a, n, nmax);
     }
+};
+template <int S, int K, int P>
+struct MergeUp<S, K, P, false> {
+    static NL_HD void run(float *, int, int) {}
 };
 template <int S, int P>
-struct SortMerges<S, 1, P> {
-    static NL_HD void run(float *, int) {}
-};
+NL_HD void sort_static(float *a, int n, int nmax) {
+    sort_blocks16<S, true>(a, n, nmax);
+    MergeUp<S, 32, P>::run(a, n, nmax);
+}
 
 template <int S>
 NL_HD void sort_column(float *a, int n, int nmax) {
     // (no NaNs and min/max instead of a swap: an exchange of equal values or of -0/+0 cannot be seen
     // in the sorted sequence of values)
-    if (nmax <= 32) { SortMerges<S, 32, 32>::run(a, n); return; }
-    if (nmax <= 64) { SortMerges<S, 64, 64>::run(a, n); return; }
-    if (nmax <= 128) { SortMerges<S, 128, 128>::run(a, n); return; }
-    if (nmax <= 256) { SortMerges<S, 256, 256>::run(a, n); return; }
+    if (nmax <= 32) { sort_static<S, 32>(a, n, nmax); return; }
+    if (nmax <= 64) { sort_static<S, 64>(a, n, nmax); return; }
+    if (nmax <= 128) { sort_static<S, 128>(a, n, nmax); return; }
+    if (nmax <= 256) { sort_static<S, 256>(a, n, nmax); return; }
     int P = 512;
     while (P < nmax) P <<= 1;
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int s = k >> 1; s >= 1; s >>= 1) {
+    sort_blocks16<S, true>(a, n, nmax);
+    for (int k = 32; k <= P; k <<= 1) {
+        for (int s = k >> 1; s >= 16; s >>= 1) {
             const bool mirror = s == (k >> 1);
 #pragma unroll 4
             for (int i = 0; i < (P >> 1); i++) {
@@ -576,6 +623,7 @@ NL_HD void sort_column(float *a, int n, int nmax) {
                 }
             }
         }
+        sort_blocks16<S, false>(a, n, nmax);
     }
 }
 
