@@ -78,7 +78,11 @@ int  nl_stack_put_frame(nl_stack_job *job, int32_t i, const float *host, int64_t
 int  nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_stride);   /* device-resident producers */
 /* Runs one stacking pass.  mode/sigma/ref_frame_loc are OpStack's fields (stack.go:66-73); weights is
  * NULL (StWeightNone) or n_frames floats from nl_get_weights.  The result (pixels floats) and the two
- * clip counters (stack.go:140, widened to 64 bit) go to host memory; blocks until they are there. */
+ * clip counters (stack.go:140, widened to 64 bit) go to host memory; blocks until they are there.
+ * Device memory: the sigma, winsorized-sigma and linear-fit modes keep a pool for columns whose late clipping
+ * passes are finished by follow-up launches: up to 25 % of the job's frame bytes (125 % for the
+ * linear fit), never more than half of the free device memory, allocated on the first such run and kept with the
+ * job; without room for it the modes run in one launch. */
 int  nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                   float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
 /* OpStack.Apply in ONE call for hosts that can pass all frame pointers at once: host_frames[i] points to frame
