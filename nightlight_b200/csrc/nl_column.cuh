@@ -754,7 +754,12 @@ NL_HD float reduce_linfit(float *g, int &cur, int nmax, const float *ramp, float
     for (int i = 0; i < cur; i++) ysum = nl_addf(ysum, g[i * S]);
     int round = 0;
     while (NL_ANY(!done)) {
-        if (max_iters > 0 && round == max_iters) break;
+        if (max_iters > 0 && round == max_iters) {
+            // a column the last round emptied is not handed on (an empty column means "no samples" to the caller):
+            // its next round is mean = 0/0 and nothing left to reject
+            if (!done && cur == 0) { mean = nl_divf(ysum, 0.0f); done = true; }
+            break;
+        }
         round++;
         const int m = done ? 0 : cur;
         // LinearRegression(xs, ys), stats.go:569-586

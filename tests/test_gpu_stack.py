@@ -288,7 +288,7 @@ def test_stack_apply_one_call_striped(ctx):
     assert rc == nl.binding.NL_E_INVALID and b"invalid stacking mode" in lib.nl_last_error()
 
 
-@pytest.mark.parametrize("seed", [20261017, 1, 2, 3])
+@pytest.mark.parametrize("seed", [20261017, 1, 2, 3, 112, 124])     # 112, 124: a linear fit that rejects every sample at a deferral boundary
 def test_random_shapes_and_modes_fuzz(ctx, seed):
     """seeded fuzz over frame counts, pixel counts (ragged tiles, unaligned rows -> both staging paths),
     NaN densities, outliers, sigmas and modes: every result bit-identical to the oracle"""
