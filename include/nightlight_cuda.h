@@ -160,6 +160,11 @@ int  nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32
  * stats = the frame's MedianDiffStats (min, mean, max, stddev). */
 int  nl_op_bad_pixel(nl_ctx *ctx, float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
                      int64_t *removed, float stats[4]);
+/* The same for a frame that is already resident: dev_data holds the pixels of host_data; both copies are repaired,
+ * so the operators that follow (nl_estimate_noise_dev, nl_find_stars_dev, nl_project_dev / _scatter_dev) work on
+ * the device copy without another upload. */
+int  nl_op_bad_pixel_dev(nl_ctx *ctx, float *dev_data, float *host_data, int64_t len, int32_t width, float sigma_low,
+                         float sigma_high, int64_t *removed, float stats[4]);
 
 /* ---- batches: replaces StackIncremental / StackIncrementalFinalize (stack.go:924-944) -------
  * acc = light*weight (first != 0) or acc += light*weight; then acc *= 1/weight_sum.  Device buffers. */
@@ -215,6 +220,11 @@ int  nl_find_bright_dev(nl_ctx *ctx, const float *dev_data, int32_t len, int32_t
 int  nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float location, float scale,
                    float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
                    nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr);
+/* FindStars on a resident frame: the full-frame scan reads dev_data, the sparse per-star steps read host_data
+ * (the same pixels). */
+int  nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data, int32_t len, int32_t width, float location,
+                       float scale, float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
+                       nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr);
 
 /* ---- synthetic frames (the workload generator, not reference code) --- */
 int  nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64_t count, uint32_t frame, uint32_t seed);

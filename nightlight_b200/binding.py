@@ -70,6 +70,9 @@ DECLARED_SYMBOLS = {
     "nl_bad_pixel_map": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, _i32p, C.c_int64, _i64p, _fp]),
     "nl_bad_pixel_map_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, _vp, _i32p, C.c_int64, _i64p, _fp]),
     "nl_op_bad_pixel": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, _i64p, _fp]),
+    "nl_op_bad_pixel_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_float, C.c_float, _i64p, _fp]),
+    "nl_find_stars_dev": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32] + [C.c_float] * 5 + [C.c_int32, C.c_float, _vp, C.c_int32,
+                                    _i32p, _fp, _fp]),
     "nl_stack_incremental_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_int]),
     "nl_stack_incremental_finalize_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_float]),
     "nl_transform_invert": (C.c_int, [_fp, _fp]),

@@ -38,6 +38,21 @@ int ensure_scratch(nl_ctx *ctx, size_t bytes) {
     return NL_OK;
 }
 
+int ensure_frame(nl_ctx *ctx, int slot, size_t bytes, float **out) {
+    if (ctx->frame_bytes[slot] < bytes) {
+        if (ctx->frame[slot]) {
+            NL_CUDA(cudaStreamSynchronize(ctx->stream));
+            NL_CUDA(cudaFree(ctx->frame[slot]));
+            ctx->frame[slot] = nullptr;
+            ctx->frame_bytes[slot] = 0;
+        }
+        NL_CUDA(cudaMalloc(&ctx->frame[slot], bytes + 256));
+        ctx->frame_bytes[slot] = bytes;
+    }
+    *out = (float *)ctx->frame[slot];
+    return NL_OK;
+}
+
 }  // namespace nl
 
 using namespace nl;
@@ -88,6 +103,8 @@ int nl_ctx_destroy(nl_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->list) cudaFree(ctx->list);
+    for (int k = 0; k < 2; k++)
+        if (ctx->frame[k]) cudaFree(ctx->frame[k]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return NL_OK;

@@ -24,6 +24,8 @@ struct nl_ctx {
     // scratch owned by the context, grown on demand (star scan)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *frame[2] = {nullptr, nullptr};   // whole-frame staging of the host-pointer entry points (grown on demand, kept)
+    size_t frame_bytes[2] = {0, 0};
     void *list = nullptr;            // candidate list of the star scan (kept apart from `scratch`, which holds the row offsets)
     size_t list_bytes = 0;
     // nl_stack_apply keeps its two stripe lanes (context + job + result buffer each) between calls:
@@ -40,6 +42,7 @@ namespace nl {
 int set_error(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int ensure_scratch(nl_ctx *ctx, size_t bytes);
+int ensure_frame(nl_ctx *ctx, int slot, size_t bytes, float **out);     // nl_api.cu
 int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total);   // nl_stars.cu
 void median_filter_sparse_host(float *data, int32_t len, int32_t width, const int32_t *indices, int64_t n);     // nl_stars.cu
 int fits_decode_launch(nl_ctx *ctx, const void *dev_raw, int bitpix, long long n, float bscale, float bzero, float *dev_dst);

@@ -221,11 +221,10 @@ int nl_estimate_noise(nl_ctx *ctx, const float *host_data, int32_t len, int32_t 
     NL_REQUIRE(host_data || len == 0, "NULL data");
     CtxGuard g(ctx);
     float *dev = nullptr;
-    NL_CUDA(cudaMalloc(&dev, sizeof(float) * (size_t)(len > 0 ? len : 1)));
-    cudaError_t e = cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = e == cudaSuccess ? nl_estimate_noise_dev(ctx, dev, 1, len, width, len / width, noise) : cuda_fail(e, "noise upload");
-    cudaFree(dev);
-    return rc;
+    int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)(len > 0 ? len : 1), &dev);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    return nl_estimate_noise_dev(ctx, dev, 1, len, width, len / width, noise);
 }
 
 }  // extern "C"

@@ -595,11 +595,10 @@ int nl_stats(nl_ctx *ctx, const float *host_data, int64_t len, float stats[4]) {
     NL_REQUIRE(ctx && host_data && stats && len >= 1, "bad argument");
     CtxGuard g(ctx);
     float *dev = nullptr;
-    NL_CUDA(cudaMalloc(&dev, sizeof(float) * (size_t)len));
-    cudaError_t e = cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = e == cudaSuccess ? stats_dev(ctx, dev, len, stats) : cuda_fail(e, "stats upload");
-    cudaFree(dev);
-    return rc;
+    int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &dev);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    return stats_dev(ctx, dev, len, stats);
 }
 
 // BadPixelMap on a device frame.  dev_tmp (len floats) receives data - median3x3(data).
@@ -650,36 +649,84 @@ int nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t w
                      int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]) {
     NL_REQUIRE(ctx && host_data && len >= 1, "bad argument");
     CtxGuard g(ctx);
-    float *dev = nullptr;
-    const size_t bytes = sizeof(float) * (size_t)len, off = (bytes + 255) & ~(size_t)255;
-    NL_CUDA(cudaMalloc(&dev, 2 * off));
-    cudaError_t e = cudaMemcpyAsync(dev, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = e == cudaSuccess ? nl_bad_pixel_map_dev(ctx, dev, len, width, sigma_low, sigma_high, (float *)((char *)dev + off),
-                                                     host_bpm, cap, count, stats)
-                              : cuda_fail(e, "bad-pixel map upload");
-    cudaFree(dev);
-    return rc;
+    float *dev = nullptr, *tmp = nullptr;
+    const size_t bytes = sizeof(float) * (size_t)len;
+    int rc = ensure_frame(ctx, 0, bytes, &dev);
+    if (rc == NL_OK) rc = ensure_frame(ctx, 1, bytes, &tmp);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(dev, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return nl_bad_pixel_map_dev(ctx, dev, len, width, sigma_low, sigma_high, tmp, host_bpm, cap, count, stats);
+}
+
+// scatter of repaired pixels into the device copy of a frame
+__global__ void patch_kernel(float *__restrict__ data, const int32_t *__restrict__ idx, const float *__restrict__ val, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) data[idx[i]] = val[i];
+}
+
+// OpBadPixel.Apply for monochrome frames, preprocess.go:180-191: BadPixelMap on the device, then the listed pixels
+// repaired in place (sparse and sequential: on the host).  host_data is updated; *removed = len(bpm).
+static int op_bad_pixel(nl_ctx *ctx, float *dev_data, bool upload, float *host_data, int64_t len, int32_t width, float sigma_low,
+                        float sigma_high, int64_t *removed, float stats[4]) {
+    NL_REQUIRE(ctx && host_data && removed && stats && len >= 1 && width > 0, "bad argument");
+    *removed = 0;
+    if (sigma_low == 0.0f || sigma_high == 0.0f) return NL_OK;          // :181-183
+    CtxGuard g(ctx);
+    const size_t bytes = sizeof(float) * (size_t)len;
+    float *tmp = nullptr;
+    int rc = ensure_frame(ctx, 1, bytes, &tmp);
+    if (rc != NL_OK) return rc;
+    if (upload) {
+        rc = ensure_frame(ctx, 0, bytes, &dev_data);
+        if (rc != NL_OK) return rc;
+        NL_CUDA(cudaMemcpyAsync(dev_data, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int64_t cap = len / 100 + 1024, count = 0;                          // badpixels.go:42
+    std::vector<int32_t> bpm((size_t)cap);
+    rc = nl_bad_pixel_map_dev(ctx, dev_data, len, width, sigma_low, sigma_high, tmp, bpm.data(), cap, &count, stats);
+    if (rc == NL_OK && count > cap) {
+        cap = count;
+        bpm.resize((size_t)cap);
+        rc = nl_bad_pixel_map_dev(ctx, dev_data, len, width, sigma_low, sigma_high, tmp, bpm.data(), cap, &count, stats);
+    }
+    if (rc != NL_OK) return rc;
+    median_filter_sparse_host(host_data, (int32_t)len, width, bpm.data(), count);
+    *removed = count;
+    if (!upload && count > 0) {
+        // keep the device copy identical to the repaired host frame: scatter the final values of the repaired pixels
+        // (a pixel listed once has one final value; the list is ascending and duplicate-free)
+        std::vector<float> val((size_t)count);
+        for (int64_t k = 0; k < count; k++) val[(size_t)k] = host_data[bpm[(size_t)k]];
+        const long long slots = (count + 63) & ~63ll;
+        if ((size_t)(2 * slots) * 4 > bytes) {                          // more than half the frame is bad: send it whole
+            NL_CUDA(cudaMemcpyAsync(dev_data, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            int32_t *didx = (int32_t *)tmp;                             // the difference image is not needed any more
+            float *dval = tmp + slots;
+            NL_CUDA(cudaMemcpyAsync(didx, bpm.data(), sizeof(int32_t) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+            NL_CUDA(cudaMemcpyAsync(dval, val.data(), sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+            patch_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(dev_data, didx, dval, count);
+            NL_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));                    // bpm and val go out of scope
+    }
+    return NL_OK;
 }
 
 // OpBadPixel.Apply for monochrome frames, preprocess.go:180-191: BadPixelMap on the device, then the listed pixels
 // repaired in place (sparse and sequential: on the host).  host_data is updated; *removed = len(bpm).
 int nl_op_bad_pixel(nl_ctx *ctx, float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
                     int64_t *removed, float stats[4]) {
-    NL_REQUIRE(ctx && host_data && removed && stats && len >= 1 && width > 0, "bad argument");
-    *removed = 0;
-    if (sigma_low == 0.0f || sigma_high == 0.0f) return NL_OK;          // :181-183
-    int64_t cap = len / 100 + 1024, count = 0;                          // badpixels.go:42
-    std::vector<int32_t> bpm((size_t)cap);
-    int rc = nl_bad_pixel_map(ctx, host_data, len, width, sigma_low, sigma_high, bpm.data(), cap, &count, stats);
-    if (rc == NL_OK && count > cap) {
-        cap = count;
-        bpm.resize((size_t)cap);
-        rc = nl_bad_pixel_map(ctx, host_data, len, width, sigma_low, sigma_high, bpm.data(), cap, &count, stats);
-    }
-    if (rc != NL_OK) return rc;
-    median_filter_sparse_host(host_data, (int32_t)len, width, bpm.data(), count);
-    *removed = count;
-    return NL_OK;
+    return op_bad_pixel(ctx, nullptr, true, host_data, len, width, sigma_low, sigma_high, removed, stats);
+}
+
+// The same with the frame already resident (dev_data holds the pixels of host_data): both copies are repaired, so
+// the operators that follow (noise estimate, star detection, resample) run on the device copy without a new upload.
+int nl_op_bad_pixel_dev(nl_ctx *ctx, float *dev_data, float *host_data, int64_t len, int32_t width, float sigma_low,
+                        float sigma_high, int64_t *removed, float stats[4]) {
+    NL_REQUIRE(dev_data, "NULL device frame");
+    return op_bad_pixel(ctx, dev_data, false, host_data, len, width, sigma_low, sigma_high, removed, stats);
 }
 
 }  // extern "C"

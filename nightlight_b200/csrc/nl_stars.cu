@@ -435,9 +435,11 @@ int nl_find_bright(nl_ctx *ctx, const float *host_data, int32_t len, int32_t wid
     return rc;
 }
 
-int nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float location, float scale,
-                  float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
-                  nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr) {
+// FindStars with the frame already on the device (dev_data) and in host memory (host_data, the same pixels): the
+// full-frame scan reads the device copy, the sparse per-star steps the host copy
+int nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data, int32_t len, int32_t width, float location,
+                      float scale, float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
+                      nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr) {
     NL_REQUIRE(ctx && count && sum_of_shifts && avg_hfr, "NULL argument");
     NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
     NL_REQUIRE(out || cap == 0, "out is NULL");
@@ -445,20 +447,14 @@ int nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t widt
     const float threshold = location + scale * star_sig;
     int32_t n = 0;
     *count = 0; *sum_of_shifts = 0.0f; *avg_hfr = 0.0f;
-    NL_REQUIRE(host_data || len == 0, "data is NULL");
+    NL_REQUIRE((host_data && dev_data) || len == 0, "data is NULL");
     CtxGuard g(ctx);
     std::vector<nl_star> stars(1);
     if (len > 0) {
-        float *dev = nullptr;
-        NL_CUDA(cudaMalloc(&dev, sizeof(float) * (size_t)len));
-        cudaError_t e = cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
-        int rc = e == cudaSuccess ? bright_count(ctx, dev, len, width, threshold, radius, &n) : cuda_fail(e, "cudaMemcpyAsync");
-        if (rc == NL_OK) {
-            stars.resize((size_t)(n > 0 ? n : 1));
-            rc = bright_write(ctx, dev, len, width, threshold, radius, stars.data(), n);
-        }
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(dev);
+        int rc = bright_count(ctx, dev_data, len, width, threshold, radius, &n);
+        if (rc != NL_OK) return rc;
+        stars.resize((size_t)(n > 0 ? n : 1));
+        rc = bright_write(ctx, dev_data, len, width, threshold, radius, stars.data(), n);
         if (rc != NL_OK) return rc;
     }
     int m = n;
@@ -472,6 +468,21 @@ int nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t widt
     for (int i = 0; i < m && i < cap; i++) out[i] = stars[i];
     *count = m;
     return NL_OK;
+}
+
+int nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float location, float scale,
+                  float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
+                  nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr) {
+    NL_REQUIRE(ctx && len >= 0 && (host_data || len == 0), "bad argument");
+    CtxGuard g(ctx);
+    float *dev = nullptr;
+    if (len > 0) {
+        int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &dev);
+        if (rc != NL_OK) return rc;
+        NL_CUDA(cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return nl_find_stars_dev(ctx, dev, host_data, len, width, location, scale, star_sig, bp_sigma, star_in_out, radius,
+                             median_diff_stddev, out, cap, count, sum_of_shifts, avg_hfr);
 }
 
 }  // extern "C"

@@ -143,3 +143,47 @@ def test_star_detection_threshold_from_device_stats(ctx):
     stars, shifts, hfr = nl.find_stars(ctx, img, w, loc, scale, 10.0, 5.0, 1.4, 12, float(st[3]))
     want = O.find_stars(img, w, loc, scale, 10.0, 5.0, 1.4, 12, float(want_st[3]))
     assert len(stars) == len(want[0]) and len(stars) > 5
+
+
+def test_resident_frame_pipeline_one_upload(ctx):
+    """bad-pixel repair -> noise estimate -> star detection on ONE upload of the frame: the `_dev` entry points keep the
+    device copy in step with the host copy (the repaired pixels are scattered into it), results equal the host-call
+    sequence and the oracle"""
+    import ctypes as C
+    from nightlight_b200.binding import check, load_library
+    from test_gpu_project_stars import star_field
+    lib = load_library()
+    w, h = 480, 360
+    img = star_field(w, h, 30, seed=31, hot=80).astype(np.float32).ravel()
+    host = img.copy()
+    dev = ctx.dev_alloc(4 * host.size)
+    try:
+        ctx.h2d(dev, host)
+        st = np.zeros(4, np.float32)
+        removed = C.c_int64()
+        fp = C.POINTER(C.c_float)
+        check(lib.nl_op_bad_pixel_dev(ctx.handle, C.c_void_p(dev), host.ctypes.data_as(C.c_void_p), host.size, w, 3.0, 5.0,
+                                      C.byref(removed), st.ctypes.data_as(fp)))
+        want_img, want_removed, want_st = O.op_bad_pixel(img, w, 3.0, 5.0, amd64=True)
+        assert removed.value == want_removed and removed.value > 20
+        assert np.array_equal(host.view(np.uint32), want_img.view(np.uint32))
+        back = np.empty_like(host)
+        ctx.d2h(back, dev)
+        assert np.array_equal(back.view(np.uint32), host.view(np.uint32))          # device copy repaired too
+        noise = (C.c_float * 1)()
+        check(lib.nl_estimate_noise_dev(ctx.handle, C.c_void_p(dev), 1, host.size, w, h, noise))
+        assert np.float32(noise[0]).view(np.uint32) == O.estimate_noise(want_img, w, amd64=True).view(np.uint32)
+        loc, scale = np.float32(np.median(want_img)), np.float32(noise[0])
+        cap = 4096
+        out = np.zeros(cap, dtype=nl.STAR_DTYPE)
+        n, sos, hfr = C.c_int32(), C.c_float(), C.c_float()
+        check(lib.nl_find_stars_dev(ctx.handle, C.c_void_p(dev), host.ctypes.data_as(C.c_void_p), host.size, w, float(loc), float(scale),
+                                    8.0, 5.0, 1.4, 12, float(st[3]), out.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(sos),
+                                    C.byref(hfr)))
+        want = O.find_stars(want_img, w, loc, scale, 8.0, 5.0, 1.4, 12, float(want_st[3]))
+        assert n.value == len(want[0]) and n.value > 5
+        for f in ("index", "x", "y", "mass", "hfr"):
+            assert np.array_equal(out[:n.value][f], want[0][f]), f
+        assert np.float32(hfr.value).view(np.uint32) == want[2].view(np.uint32)
+    finally:
+        ctx.dev_free(dev)
