@@ -426,13 +426,10 @@ int nl_find_bright(nl_ctx *ctx, const float *host_data, int32_t len, int32_t wid
     if (len == 0) return NL_OK;
     CtxGuard g(ctx);
     float *dev = nullptr;
-    NL_CUDA(cudaMalloc(&dev, sizeof(float) * (size_t)len));
-    cudaError_t e = cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = e == cudaSuccess ? find_bright_dev(ctx, dev, len, width, threshold, radius, out, cap, count)
-                              : cuda_fail(e, "cudaMemcpyAsync");
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(dev);
-    return rc;
+    int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &dev);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(dev, host_data, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    return find_bright_dev(ctx, dev, len, width, threshold, radius, out, cap, count);
 }
 
 // FindStars with the frame already on the device (dev_data) and in host memory (host_data, the same pixels): the
