@@ -36,7 +36,7 @@ struct StackArgs {
     int defer_passes;        // 0: run every column to the end
     int phase;               // 0: tiles of the frame stack; >= 1: tiles of the input pool
     struct Pool {
-        float *samples;      // [cap/32][npad][32] sample columns
+        float *samples;      // [cap/S][npad][S] sample columns, S = the tile width of the launch
         void *idx;           // weighted modes: the frame-index columns, same layout
         long long *pixel;    // [cap] pixel of a slot
         int *cur;            // [cap] survivors of a slot
@@ -110,14 +110,14 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
     IDX *gw = reinterpret_cast<IDX *>(region + (size_t)4 * (MODE == ST_MAD ? 2 : 1) * S * npad) + (lane % S);
     (void)sc; (void)gw;
 
-    constexpr bool DEFER = S == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT);
+    constexpr bool DEFER = MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT;
     const bool pool_phase = DEFER && a.phase >= 1;
     long long pool_slots = 0;
     if (pool_phase) {
         const unsigned long long c = *a.pool_in.count;
         pool_slots = c < (unsigned long long)a.pool_in.cap ? (long long)c : a.pool_in.cap;
     }
-    const long long tiles = pool_phase ? (pool_slots + 31) / 32 : (a.pixels + S - 1) / S;
+    const long long tiles = pool_phase ? (pool_slots + S - 1) / S : (a.pixels + S - 1) / S;
     int ncl = 0, nch = 0;
 
     // one mbarrier per warp for the TMA staging, in the last 64 bytes of the last gap (32-pixel tiles only:
@@ -145,24 +145,26 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
         int cur = 0;
         bool negzero = false;            // median mode: a -0.0 sample makes the SIGN of a zero median depend on the permutation
         if (pool_phase) {
-            // a tile of the pool: 32 deferred columns, laid out [sample][slot] like a slab
-            const long long slot = t * 32 + lane;
-            valid = slot < pool_slots;
+            // a tile of the pool: S deferred columns, laid out [sample][slot] like a slab
+            const long long slot = t * S + lane;
+            valid = lane < S && slot < pool_slots;
             p = valid ? a.pool_in.pixel[slot] : 0;
             cur = valid ? a.pool_in.cur[slot] : 0;
             const int rows = __reduce_max_sync(0xffffffffu, cur);
-            const float *src = a.pool_in.samples + t * ((long long)npad * 32) + lane;
-            for (int i0 = 0; i0 < rows; i0 += 32) {               // 32 row segments of 128 bytes in flight per warp
+            const float *src = a.pool_in.samples + t * ((long long)npad * S) + lane;
+            for (int i0 = 0; i0 < rows; i0 += 32) {               // 32 row segments in flight per warp
                 float v[32];
 #pragma unroll
-                for (int u = 0; u < 32; u++) v[u] = ld_stream(src + (long long)(i0 + u) * 32);     // (npad is a multiple of 32)
+                for (int u = 0; u < 32; u++) v[u] = lane < S ? ld_stream(src + (long long)(i0 + u) * S) : 0.0f;   // (npad is a multiple of 32)
+                if (lane < S) {
 #pragma unroll
-                for (int u = 0; u < 32; u++) g[(i0 + u) * S] = v[u];
+                    for (int u = 0; u < 32; u++) g[(i0 + u) * S] = v[u];
+                }
             }
-            if (W) {
-                const IDX *srcw = reinterpret_cast<const IDX *>(a.pool_in.idx) + t * ((long long)npad * 32) + lane;
+            if (W && lane < S) {
+                const IDX *srcw = reinterpret_cast<const IDX *>(a.pool_in.idx) + t * ((long long)npad * S) + lane;
 #pragma unroll 8
-                for (int i = 0; i < rows; i++) gw[i * S] = srcw[(long long)i * 32];
+                for (int i = 0; i < rows; i++) gw[i * S] = srcw[(long long)i * S];
             }
         } else if (tma_tiles) {
             // (the slab was last touched by this warp's generic-proxy loads and stores: order them
@@ -249,11 +251,11 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
                 const long long slot = (long long)base + __popc(pm & ((1u << lane) - 1u));
                 spilled = pending && slot < a.pool_out.cap;
                 if (spilled) {
-                    float *dst = a.pool_out.samples + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
-                    for (int i = 0; i < c; i++) dst[(long long)i * 32] = g[i * S];
+                    float *dst = a.pool_out.samples + (slot / S) * ((long long)npad * S) + (slot % S);
+                    for (int i = 0; i < c; i++) dst[(long long)i * S] = g[i * S];
                     if (W) {
-                        IDX *dstw = reinterpret_cast<IDX *>(a.pool_out.idx) + (slot >> 5) * ((long long)npad * 32) + (slot & 31);
-                        for (int i = 0; i < c; i++) dstw[(long long)i * 32] = gw[i * S];
+                        IDX *dstw = reinterpret_cast<IDX *>(a.pool_out.idx) + (slot / S) * ((long long)npad * S) + (slot % S);
+                        for (int i = 0; i < c; i++) dstw[(long long)i * S] = gw[i * S];
                     }
                     a.pool_out.pixel[slot] = p;
                     a.pool_out.cur[slot] = c;
@@ -406,6 +408,36 @@ inline bool ensure_pools(nl_stack_job *job, int idx_bytes, const double frac[2],
     return true;
 }
 
+// One launch, or -- deferral of late passes (see StackArgs) -- launch 0 over the frame stack and one launch per pool
+// generation.
+template <int MODE, bool W, int S, typename IDX>
+inline int launch_deferred(nl_stack_job *job, const StackArgs &args) {
+    if (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT) {
+        DeferSchedule d = defer_schedule(MODE);
+        // several regrouping launches only pay with many tiles per warp (each launch ends in a tail of half-idle SMs):
+        // measured, 1024 frames x 65 536 pixels: 15.5 ms in one launch, 16.6 ms with six regroupings; x 1 M pixels: 223 -> 213 ms
+        if (d.n > 1 && !getenv("NL_DEFER_PASSES") && (job->pixels + S - 1) / S < 32ll * job->ctx->sm_count * 8) d.n = 0;
+        StackArgs::Pool pools[2];
+        if (d.n > 0 && ensure_pools(job, W ? (int)sizeof(IDX) : 0, d.frac, pools)) {
+            StackArgs a2 = args;
+            const int rounds = pools[1].cap >= 32 ? d.n : 1;          // without a second pool: defer once
+            for (int r = 0; r <= rounds; r++) {
+                a2.phase = r;
+                a2.defer_passes = r < rounds ? d.at[r] - (r ? d.at[r - 1] : 0) : 0;
+                a2.pool_in = pools[(r + 1) & 1];                      // what launch r-1 filled
+                a2.pool_in.count = job->clip + 3 + 2 * (r > 0 ? r - 1 : 0);
+                a2.pool_tile_counter = job->clip + 4 + 2 * (r > 0 ? r - 1 : 0);
+                a2.pool_out = pools[r & 1];
+                a2.pool_out.count = job->clip + 3 + 2 * r;
+                int rc = launch_column<MODE, W, S, IDX>(job, a2);
+                if (rc != NL_OK) return rc;
+            }
+            return NL_OK;
+        }
+    }
+    return launch_column<MODE, W, S, IDX>(job, args);
+}
+
 template <int MODE, bool W, typename IDX>
 inline int launch_column_i(nl_stack_job *job, const StackArgs &args) {
     constexpr int SB = SlotBytes<MODE, W, IDX>::value;
@@ -431,32 +463,11 @@ inline int launch_column_i(nl_stack_job *job, const StackArgs &args) {
         const int wdt = atoi(force);
         if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + 2 * gap) * wdt <= cap) best = wdt;
     }
-    if (best == 32 && (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT)) {
-        // deferral of late passes (see StackArgs): launch 0 over the frame stack, then one launch per pool generation
-        const DeferSchedule d = defer_schedule(MODE);
-        StackArgs::Pool pools[2];
-        if (d.n > 0 && ensure_pools(job, W ? (int)sizeof(IDX) : 0, d.frac, pools)) {
-            StackArgs a2 = args;
-            const int rounds = pools[1].cap >= 32 ? d.n : 1;          // without a second pool: defer once
-            for (int r = 0; r <= rounds; r++) {
-                a2.phase = r;
-                a2.defer_passes = r < rounds ? d.at[r] - (r ? d.at[r - 1] : 0) : 0;
-                a2.pool_in = pools[(r + 1) & 1];                      // what launch r-1 filled
-                a2.pool_in.count = job->clip + 3 + 2 * (r > 0 ? r - 1 : 0);
-                a2.pool_tile_counter = job->clip + 4 + 2 * (r > 0 ? r - 1 : 0);
-                a2.pool_out = pools[r & 1];
-                a2.pool_out.count = job->clip + 3 + 2 * r;
-                int rc = launch_column<MODE, W, 32, IDX>(job, a2);
-                if (rc != NL_OK) return rc;
-            }
-            return NL_OK;
-        }
-    }
     switch (best) {
-    case 32: return launch_column<MODE, W, 32, IDX>(job, args);
-    case 16: return launch_column<MODE, W, 16, IDX>(job, args);
-    case 8: return launch_column<MODE, W, 8, IDX>(job, args);
-    case 1: return launch_column<MODE, W, 1, IDX>(job, args);
+    case 32: return launch_deferred<MODE, W, 32, IDX>(job, args);
+    case 16: return launch_deferred<MODE, W, 16, IDX>(job, args);
+    case 8: return launch_deferred<MODE, W, 8, IDX>(job, args);
+    case 1: return launch_deferred<MODE, W, 1, IDX>(job, args);
     }
     return set_error(NL_E_INVALID, "n_frames %d too large for shared memory", job->n);
 }

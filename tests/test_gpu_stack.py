@@ -328,6 +328,20 @@ def test_deferred_clipping_passes_pool_and_overflow(ctx, monkeypatch, mode, weig
     check_against_oracle(ctx, frames[:40], mode, weighted)
 
 
+@pytest.mark.parametrize("defer", ["1", "3", "2,4,7"])
+@pytest.mark.parametrize("n", [520, 1030])
+def test_deferred_passes_on_narrow_tiles(ctx, monkeypatch, n, defer):
+    """more than 256 frames: 16- and 8-pixel tiles; the pools then hold tiles of that width"""
+    monkeypatch.setenv("NL_DEFER_PASSES", defer)
+    rng = np.random.default_rng(n + len(defer))
+    p = 16 * 7 + 5
+    frames = (rng.standard_t(2.0, size=(n, p)) * 25 + 500).astype(np.float32)
+    frames[rng.random((n, p)) < 0.01] = np.nan
+    frames[:, 3] = np.nan
+    for mode, weighted in (("sigma", False), ("winsor", True), ("linfit", False)):
+        check_against_oracle(ctx, frames, mode, weighted, 2.0, 2.5, ref_loc=5.0)
+
+
 def test_default_deferral_schedules_on_the_synthetic_workload(ctx):
     """the schedules the library uses by default (sigma {3}, winsor {2}, linear fit {8,...,30}), on generator data"""
     frames = O.synth_frames(128, 4096 * 100, 32 * 300)
