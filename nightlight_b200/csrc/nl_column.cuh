@@ -33,10 +33,12 @@
 #define NL_ANY(x) (__any_sync(0xffffffffu, (x)))
 #define NL_WARP_MIN(x) (__reduce_min_sync(0xffffffffu, (x)))
 #define NL_WARP_MAX(x) (__reduce_max_sync(0xffffffffu, (x)))
+#define NL_SYNCWARP() __syncwarp()
 #else
 #define NL_ANY(x) (x)
 #define NL_WARP_MIN(x) (x)
 #define NL_WARP_MAX(x) (x)
+#define NL_SYNCWARP() ((void)0)
 #endif
 
 namespace nl {
@@ -598,22 +600,50 @@ NL_HD void sort_static(float *a, int n, int nmax) {
     MergeUp<S, 32, P>::run(a, n, nmax);
 }
 
+// q, Q: a tile narrower than the warp leaves 32/S lanes per column; for the long columns that need such tiles the
+// Q = 32/S lanes of a column share the sort -- helper q takes the 16-blocks and the comparators congruent to q
+// modulo Q (comparators of one stage are independent; with the [sample][S] layout the Q helpers of all S columns
+// hit 32 different banks), one __syncwarp between stages.  Every lane passes its column's n (not its own sample
+// count).  Host and 32-pixel tiles: q = 0, Q = 1.
+template <int S, bool FULL>
+NL_HD void sort_blocks16_coop(float *a, int n, int nmax, int q, int Q) {
+    for (int b = 16 * q; b < nmax; b += 16 * Q) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = b + j < n ? a[(b + j) * S] : INFINITY;
+        if (FULL) {
+            reg_mirror<2>(v);
+            reg_mirror<4>(v); reg_clean<1>(v);
+            reg_mirror<8>(v); reg_clean<2>(v); reg_clean<1>(v);
+            reg_mirror<16>(v); reg_clean<4>(v); reg_clean<2>(v); reg_clean<1>(v);
+        } else {
+            reg_clean<8>(v); reg_clean<4>(v); reg_clean<2>(v); reg_clean<1>(v);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (b + j < n) a[(b + j) * S] = v[j];
+    }
+    NL_SYNCWARP();
+}
+
 template <int S>
-NL_HD void sort_column(float *a, int n, int nmax) {
+NL_HD void sort_column(float *a, int n, int nmax, int q = 0, int Q = 1) {
     // (no NaNs and min/max instead of a swap: an exchange of equal values or of -0/+0 cannot be seen
     // in the sorted sequence of values)
-    if (nmax <= 32) { sort_static<S, 32>(a, n, nmax); return; }
-    if (nmax <= 64) { sort_static<S, 64>(a, n, nmax); return; }
-    if (nmax <= 128) { sort_static<S, 128>(a, n, nmax); return; }
-    if (nmax <= 256) { sort_static<S, 256>(a, n, nmax); return; }
-    int P = 512;
+    if (Q == 1) {
+        if (nmax <= 32) { sort_static<S, 32>(a, n, nmax); return; }
+        if (nmax <= 64) { sort_static<S, 64>(a, n, nmax); return; }
+        if (nmax <= 128) { sort_static<S, 128>(a, n, nmax); return; }
+        if (nmax <= 256) { sort_static<S, 256>(a, n, nmax); return; }
+    }
+    int P = 32;
     while (P < nmax) P <<= 1;
-    sort_blocks16<S, true>(a, n, nmax);
+    sort_blocks16_coop<S, true>(a, n, nmax, q, Q);
     for (int k = 32; k <= P; k <<= 1) {
         for (int s = k >> 1; s >= 16; s >>= 1) {
             const bool mirror = s == (k >> 1);
 #pragma unroll 4
-            for (int i = 0; i < (P >> 1); i++) {
+            for (int i = q; i < (P >> 1); i += Q) {
                 const int lo = ((i & ~(s - 1)) << 1) | (i & (s - 1));
                 const int hi = mirror ? (lo ^ (k - 1)) : (lo | s);
                 if (hi < n) {
@@ -622,8 +652,9 @@ NL_HD void sort_column(float *a, int n, int nmax) {
                     a[hi * S] = fmaxf(x, y);
                 }
             }
+            NL_SYNCWARP();
         }
-        sort_blocks16<S, false>(a, n, nmax);
+        sort_blocks16_coop<S, false>(a, n, nmax, q, Q);
     }
 }
 
@@ -744,7 +775,17 @@ NL_HD float reduce_linfit(float *g, int &cur, int nmax, const float *ramp, float
                           bool sorted = false, int max_iters = 0, bool *pending = nullptr) {
     // max_iters > 0: stop after that many rejection rounds; *pending tells which columns are not finished.  A column's
     // state between rounds is its sorted survivors g[0..cur): calling again with sorted = true resumes it.
-    if (!sorted) sort_column<S>(g, cur, nmax);
+    if (!sorted) {
+#if defined(__CUDA_ARCH__)
+        if (S < 32) {
+            // narrow tile: the 32/S lanes that alias a column sort it together (they hold no samples of their own)
+            const int lane = threadIdx.x & 31;
+            const int n_col = __shfl_sync(0xffffffffu, cur, lane % S);
+            sort_column<S>(g, n_col, nmax, lane / S, 32 / S);
+        } else
+#endif
+            sort_column<S>(g, cur, nmax);
+    }
     float mean = 0.0f;
     bool done = cur == 0;
     // sum of the samples in index order: the first chain of MeanStdDev (stats.go:247-250).  After the first
