@@ -318,8 +318,17 @@ inline int launch_column(nl_stack_job *job, const StackArgs &args) {
     const size_t per_warp = (size_t)SB * S * ((job->n + 31) & ~31) + gap;
     const size_t cap = (size_t)ctx->max_smem_optin;
     if (per_warp + gap > cap) return set_error(NL_E_INVALID, "n_frames %d too large for shared memory at tile %d", job->n, S);
-    int warps = (int)((cap - gap) / per_warp);
-    if (warps > 8) warps = 8;
+    // warps per CTA (at most 8): the split that puts the most warps on an SM -- the kernel lives on latency hiding
+    // across warps, and e.g. 128 frames fit 13 slabs per SM: two CTAs of 6 warps beat one of 8
+    const size_t sm_bytes = (size_t)ctx->smem_per_sm;
+    int warps = 1, best_total = 0;
+    for (int w = 1; w <= 8; w++) {
+        const size_t need = per_warp * w + gap;
+        if (need > cap) break;
+        int ctas = (int)(sm_bytes / (need + 1024));               // 1 KiB per CTA is reserved by the system
+        if (ctas > 32) ctas = 32;
+        if (ctas * w >= best_total) { best_total = ctas * w; warps = w; }
+    }
     const size_t smem = per_warp * warps + gap;                   // (the tile mbarriers live in the tail of the last gap)
     auto kern = stack_column_kernel<MODE, W, S, IDX>;
     NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
