@@ -26,6 +26,8 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -152,11 +154,13 @@ template <bool AMD64, bool MAX> __device__ __forceinline__ Ext ext_join(Ext a, E
 //   S   parallel sum of the run's terms
 //   A   upper bound on the sum over the run's elements of |partial sum up to that element|, partial sums counted
 //       from the start of the run: a leaf of at most 1024 elements has A = len * (sum of magnitudes)
+//   P   upper bound on |partial sum| anywhere in the run (leaf: the sum of magnitudes)
 //   len chain elements in the run
-// join(a, b) for a before b: S = a.S + b.S, A = a.A + b.A + b.len * |a.S|, len = a.len + b.len.  At the root, u * A
+// join(a, b) for a before b: S = a.S + b.S, A = a.A + b.A + b.len * |a.S|, P = max(a.P, |a.S| + b.P), len = a.len + b.len.  At the root, u * A
 // bounds the distance of the sequentially rounded chain from the exact sum (u = 2^-53 per addition).
 struct Node {
     double S[4], A[4];
+    double P[4];            // upper bound on |partial sum| anywhere in the run, partial sums counted from its start
     Ext mn[4], mx[4];
     double len;
 };
@@ -165,6 +169,7 @@ struct StatOut {            // what the host reads back after both passes
     float mn, mean, mx, stddev;
     int mean_decided, std_decided;
     double total[2], bound[2];
+    double lane_sum[2][4], lane_pmax[2][4];     // per pass: the lanes' parallel sums and bounds on their partial sums
 };
 
 constexpr int REC_VECS = 1024;      // float4 vectors per warp (32 per thread)
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
                                                          Node *__restrict__ nodes, unsigned *__restrict__ counter,
                                                          StatOut *__restrict__ out) {
     constexpr int L = AMD64 ? 4 : 1;
-    __shared__ double sh_S[4][FOLD_WORKERS], sh_A[4][FOLD_WORKERS], sh_len[FOLD_WORKERS];
+    __shared__ double sh_S[4][FOLD_WORKERS], sh_A[4][FOLD_WORKERS], sh_P[4][FOLD_WORKERS], sh_len[FOLD_WORKERS];
     __shared__ Ext sh_mn[4][FOLD_WORKERS], sh_mx[4][FOLD_WORKERS];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,7 +254,8 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
         for (int j = 0; j < 4; j++) {
             const int s = j < L ? j : 0;
             sh_S[j][warp] = j < L ? sum[s] : 0.0;
-            sh_A[j][warp] = j < L ? len * mag[s] : 0.0;
+            sh_A[j][warp] = j < L ? (double)(AMD64 ? REC_VECS : 4 * REC_VECS) * mag[s] : 0.0;    // (a full leaf's length also for the last, shorter one)
+            sh_P[j][warp] = j < L ? mag[s] : 0.0;
             sh_mn[j][warp] = j < L ? mn[s] : ext_empty<AMD64>();
             sh_mx[j][warp] = j < L ? mx[s] : ext_empty<AMD64>();
         }
@@ -257,17 +263,18 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
     __syncthreads();
     if (threadIdx.x < 4) {                       // the eight warps of this CTA, in order, into one node
         const int j = threadIdx.x;
-        double S = 0.0, A = 0.0, len = 0.0;
+        double S = 0.0, A = 0.0, P = 0.0, len = 0.0;
         Ext tmn = ext_empty<AMD64>(), tmx = tmn;
         for (int w = 0; w < 8; w++) {
             A += sh_A[j][w] + sh_len[w] * fabs(S);
+            P = fmax(P, fabs(S) + sh_P[j][w]);
             S += sh_S[j][w];
             len += sh_len[w];
             tmn = ext_join<AMD64, false>(tmn, sh_mn[j][w]);
             tmx = ext_join<AMD64, true>(tmx, sh_mx[j][w]);
         }
         Node *nd = nodes + blockIdx.x;
-        nd->S[j] = S; nd->A[j] = A; nd->mn[j] = tmn; nd->mx[j] = tmx;
+        nd->S[j] = S; nd->A[j] = A; nd->P[j] = P; nd->mn[j] = tmn; nd->mx[j] = tmx;
         if (j == 0) nd->len = len;
         __threadfence();
     }
@@ -283,11 +290,12 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
         const int n_nodes = (int)gridDim.x;
         const int per = (n_nodes + FOLD_WORKERS - 1) / FOLD_WORKERS;
         const int lo = min(n_nodes, k * per), hi = min(n_nodes, lo + per);
-        double S = 0.0, A = 0.0, len = 0.0;
+        double S = 0.0, A = 0.0, P = 0.0, len = 0.0;
         Ext tmn = ext_empty<AMD64>(), tmx = tmn;
         const volatile Node *vn = nodes;
         for (int c = lo; c < hi; c++) {
-            const double cS = vn[c].S[j], cA = vn[c].A[j], cl = vn[c].len;
+            const double cS = vn[c].S[j], cA = vn[c].A[j], cP = vn[c].P[j], cl = vn[c].len;
+            P = fmax(P, fabs(S) + cP);
             Ext cmn, cmx;
             cmn.c = vn[c].mn[j].c; cmn.kind = vn[c].mn[j].kind; cmx.c = vn[c].mx[j].c; cmx.kind = vn[c].mx[j].kind;
             A += cA + cl * fabs(S);
@@ -296,15 +304,16 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
             tmn = ext_join<AMD64, false>(tmn, cmn);
             tmx = ext_join<AMD64, true>(tmx, cmx);
         }
-        sh_S[j][k] = S; sh_A[j][k] = A; sh_mn[j][k] = tmn; sh_mx[j][k] = tmx;
+        sh_S[j][k] = S; sh_A[j][k] = A; sh_P[j][k] = P; sh_mn[j][k] = tmn; sh_mx[j][k] = tmx;
         if (j == 0) sh_len[k] = len;
         __syncthreads();
         for (int d = 1; d < FOLD_WORKERS; d <<= 1) {
-            double nS = 0, nA = 0, nl = 0;
+            double nS = 0, nA = 0, nP = 0, nl = 0;
             Ext nmn = tmn, nmx = tmx;
             const bool act = (k % (2 * d)) == 0;
             if (act) {
                 nA = sh_A[j][k] + sh_A[j][k + d] + sh_len[k + d] * fabs(sh_S[j][k]);
+                nP = fmax(sh_P[j][k], fabs(sh_S[j][k]) + sh_P[j][k + d]);
                 nS = sh_S[j][k] + sh_S[j][k + d];
                 nl = sh_len[k] + sh_len[k + d];
                 nmn = ext_join<AMD64, false>(sh_mn[j][k], sh_mn[j][k + d]);
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
             }
             __syncthreads();
             if (act) {
-                sh_S[j][k] = nS; sh_A[j][k] = nA; sh_mn[j][k] = nmn; sh_mx[j][k] = nmx;
+                sh_S[j][k] = nS; sh_A[j][k] = nA; sh_P[j][k] = nP; sh_mn[j][k] = nmn; sh_mx[j][k] = nmx;
                 if (j == 0) sh_len[k] = nl;
             }
             __syncthreads();
@@ -322,15 +331,18 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
     *counter = 0;                                              // ready for the next pass
     // the lanes, folded like stats_amd64.s:80-84; the interval around the total
     double total = (sh_S[2][0] + sh_S[3][0]) + (sh_S[0][0] + sh_S[1][0]);
-    double bound = 0.0, m = 0.0;
-    for (int j = 0; j < 4; j++) { bound += sh_A[j][0]; m += fabs(sh_S[j][0]); }
-    // u = 2^-53 per rounded addition of the reference's chain; as much again for this kernel's own float64 sums
-    // (every one of them shorter than a leaf), head-room for second-order terms; then the three folding additions
-    bound *= 2.0 * 1.001 * 1.1102230246251565e-16;
+    double bound = 0.0, m = 0.0, pm = 0.0;
+    for (int j = 0; j < 4; j++) { bound += sh_A[j][0]; m += fabs(sh_S[j][0]); pm += sh_P[j][0]; }
+    // u = 2^-53 per rounded addition of the reference's chain: u * A.  This kernel's own float64 sums: an element passes
+    // through at most 45 additions whose results stay below its leaf's sum of magnitudes (<= A / 1024 in total: 5 % of A),
+    // and one addition per node plus the worker tree at prefix level (results <= P).  Head-room for second-order terms;
+    // then the three folding additions.
+    bound = (1.05 * bound + ((double)gridDim.x + 400.0) * pm) * (1.001 * 1.1102230246251565e-16);
     bound += 8.0 * 2.220446049250313e-16 * (m + bound);
     bound = bound * 1.000001 + 2.2250738585072014e-308;
     out->total[MODE] = total;
     out->bound[MODE] = bound;
+    for (int j = 0; j < 4; j++) { out->lane_sum[MODE][j] = sh_S[j][0]; out->lane_pmax[MODE][j] = sh_P[j][0]; }
     const double dn = (double)n;
     const int n_tail = AMD64 ? 0 : (int)(n - 4 * n_vecs);       // a ragged pure-Go array: its last elements continue the chain
     const float *tail = reinterpret_cast<const float *>(data) + 4 * n_vecs;
@@ -362,6 +374,44 @@ __global__ void __launch_bounds__(256) stats_pass_kernel(const float4 *__restric
         const float slo = __double2float_rn(__dsqrt_rn(__ddiv_rn(lo, dn))), shi = __double2float_rn(__dsqrt_rn(__ddiv_rn(hi, dn)));
         out->stddev = slo;                                      // stats.go:147-149
         out->std_decided = bound == bound && dev_f32_bits(slo) == dev_f32_bits(shi);
+    }
+}
+
+// Second-level proof for sums with heavy cancellation (a mean many orders below the spread of the data: the
+// interval above is relative to the magnitudes summed, far wider than the float32 grid of such a mean).  Let
+// G = 2^g be the ulp of the largest binade any partial sum of the chain can reach (from Node::P).  A term that is a
+// multiple of G is added without rounding to a partial sum that is a multiple of G, in any order; only "fine" terms
+// (lowest set bit below G) start rounding, and each of them accounts for at most one geometric series of roundings
+// bounded by G in the reference's chain and by 2G in the parallel sum.  So |chain - parallel sum| <= 3 * G * (number of
+// fine terms) per lane -- zero for data on a grid (camera ADUs, differences of them), a few dozen ulps otherwise.
+// This kernel counts the fine terms per lane.
+template <bool AMD64, int MODE>
+__global__ void __launch_bounds__(256) stats_fine_count_kernel(const float4 *__restrict__ data, long long n_vecs, float mean, int g0,
+                                                               int g1, int g2, int g3, unsigned long long *__restrict__ counts) {
+    const int g[4] = {g0, AMD64 ? g1 : g0, AMD64 ? g2 : g0, AMD64 ? g3 : g0};
+    unsigned cnt[4] = {0, 0, 0, 0};
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n_vecs; v += (long long)gridDim.x * blockDim.x) {
+        const float4 q = __ldcs(data + v);
+        const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double t = stat_term<MODE>(e[j], mean);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+            const int ex = (int)((bits >> 52) & 0x7ff);
+            const unsigned long long mant = bits & 0xfffffffffffffull;
+            int lsb;                                                  // exponent of the lowest set bit of t
+            if (ex == 0x7ff) lsb = -100000;                           // Inf / NaN: never provable
+            else if (ex == 0) lsb = mant ? -1074 + (__ffsll((long long)mant) - 1) : 100000;     // zero adds nothing
+            else lsb = ex - 1075 + (__ffsll((long long)(mant | (1ull << 52))) - 1);
+            cnt[AMD64 ? j : 0] += lsb < g[j] ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        unsigned c = cnt[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + j, (unsigned long long)c);
     }
 }
 
@@ -456,7 +506,7 @@ static int stats_dev(nl_ctx *ctx, const float *dev, long long n, float out[4]) {
     const int n_tail = (int)(n - 4 * n_vecs);
     const unsigned grid = (unsigned)std::max<long long>(1, (n_vecs + 8 * REC_VECS - 1) / (8 * REC_VECS));
     const size_t node_bytes = ((size_t)grid * sizeof(Node) + 255) & ~(size_t)255;
-    int rc = ensure_scratch(ctx, node_bytes + 1024);
+    int rc = ensure_scratch(ctx, node_bytes + 1280);
     if (rc != NL_OK) return rc;
     Node *nodes = (Node *)ctx->scratch;
     StatOut *dout = (StatOut *)((char *)ctx->scratch + node_bytes);
@@ -506,10 +556,71 @@ static int stats_dev(nl_ctx *ctx, const float *dev, long long n, float out[4]) {
     NL_CUDA(cudaMemcpyAsync(&h, dout, sizeof(StatOut), cudaMemcpyDeviceToHost, ctx->stream));
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     const double dn = (double)n;
+    if (getenv("NL_STATS_DEBUG"))
+        fprintf(stderr, "nl_stats: n=%lld amd64=%d mean_decided=%d total0=%.17g bound0=%.3g (rel %.3g) std_decided=%d total1=%.17g bound1=%.3g (rel %.3g)\n",
+                n, (int)amd64, h.mean_decided, h.total[0], h.bound[0], h.bound[0] / fabs(h.total[0]), h.std_decided, h.total[1], h.bound[1],
+                h.bound[1] / fabs(h.total[1]));
+    // second-level proof (see stats_fine_count_kernel): the chain total of pass `mode` from the parallel lane sums when
+    // few terms can round at all.  true: *total is within a proven distance that does not change the float32 result.
+    unsigned long long *dcounts = (unsigned long long *)((char *)dout + 768);
+    auto prove = [&](int mode, float mean, const StatOut &so, double *total) -> int {       // 1 proven, 0 not, < 0 error
+        int g[4];
+        for (int j = 0; j < 4; j++) {
+            const double p = so.lane_pmax[mode][j] * 1.0000001;
+            if (!(p == p) || p > 1e300) return 0;
+            g[j] = (p > 0.0 ? ilogb(p) + 1 : -1074) + 1 - 53 + 1;       // ulp of the binade above 2 * max |partial sum|
+        }
+        if (cudaMemsetAsync(dcounts, 0, 4 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) return -1;
+        const unsigned cgrid = (unsigned)std::min<long long>(std::max<long long>(1, (n_vecs + 255) / 256), (long long)ctx->sm_count * 8);
+        if (amd64) {
+            if (mode == 0) stats_fine_count_kernel<true, 0><<<cgrid, 256, 0, ctx->stream>>>(d4, n_vecs, mean, g[0], g[1], g[2], g[3], dcounts);
+            else stats_fine_count_kernel<true, 1><<<cgrid, 256, 0, ctx->stream>>>(d4, n_vecs, mean, g[0], g[1], g[2], g[3], dcounts);
+        } else {
+            if (mode == 0) stats_fine_count_kernel<false, 0><<<cgrid, 256, 0, ctx->stream>>>(d4, n_vecs, mean, g[0], g[1], g[2], g[3], dcounts);
+            else stats_fine_count_kernel<false, 1><<<cgrid, 256, 0, ctx->stream>>>(d4, n_vecs, mean, g[0], g[1], g[2], g[3], dcounts);
+        }
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        ctx->launches++;
+        unsigned long long counts[4];
+        if (cudaMemcpyAsync(counts, dcounts, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+        if (n_tail && cudaMemcpyAsync(tail, dev + 4 * n_vecs, sizeof(float) * n_tail, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+        double b = 0.0;
+        for (int j = 0; j < (amd64 ? 4 : 1); j++) b += 4.0 * (double)counts[j] * ldexp(1.0, g[j]);
+        const double *ls = so.lane_sum[mode];
+        double t = amd64 ? (ls[2] + ls[3]) + (ls[0] + ls[1]) : ls[0];
+        if (b > 0.0) b += 4.0 * DBL_EPSILON * (fabs(ls[0]) + fabs(ls[1]) + fabs(ls[2]) + fabs(ls[3]) + b);      // the lane fold
+        auto finish = [&](double v) {
+            for (int i = 0; i < n_tail; i++) {
+                if (mode == 0) v += (double)tail[i];
+                else { volatile float d = tail[i] - mean; const double dd = (double)d; volatile double sq = dd * dd; v += sq; }
+            }
+            return mode == 0 ? (float)(v / dn) : (float)sqrt(v / dn);
+        };
+        double lo = t - b, hi = t + b;
+        if (mode == 1 && lo < 0.0) lo = 0.0;
+        const float flo = finish(lo), fhi = finish(hi);
+        uint32_t ulo, uhi;
+        memcpy(&ulo, &flo, 4); memcpy(&uhi, &fhi, 4);
+        if (getenv("NL_STATS_DEBUG"))
+            fprintf(stderr, "nl_stats: second-level proof pass %d: fine terms %llu %llu %llu %llu, grid 2^%d, bound %.3g -> %s\n", mode, counts[0],
+                    counts[1], counts[2], counts[3], g[0], b, ulo == uhi ? "proven" : "not proven");
+        if (ulo != uhi) return 0;
+        *total = t;                               // (without the tail: the caller appends it like the replay path does)
+        return 1;
+    };
+    const bool force_replay = getenv("NL_STATS_FORCE_REPLAY") != nullptr;      // development override: time the in-order replay
+    if (force_replay) h.mean_decided = h.std_decided = 0;
     if (!h.mean_decided) {
         double t;
-        rc = replay(0, 0.0f, &t);
-        if (rc != NL_OK) return rc;
+        const int proven = force_replay ? 0 : prove(0, 0.0f, h, &t);
+        if (proven < 0) return cuda_fail(cudaGetLastError(), "second-level proof");
+        if (proven) {
+            for (int i = 0; i < n_tail; i++) t += (double)tail[i];
+        } else {
+            rc = replay(0, 0.0f, &t);
+            if (rc != NL_OK) return rc;
+        }
         h.mean = (float)(t / dn);
         NL_CUDA(cudaMemcpyAsync(&dout->mean, &h.mean, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         pass1();
@@ -518,11 +629,18 @@ static int stats_dev(nl_ctx *ctx, const float *dev, long long n, float out[4]) {
         NL_CUDA(cudaMemcpyAsync(&h, dout, sizeof(StatOut), cudaMemcpyDeviceToHost, ctx->stream));
         NL_CUDA(cudaStreamSynchronize(ctx->stream));
         h.mean = mean;
+        if (force_replay) h.std_decided = 0;
     }
     if (!h.std_decided) {
         double t;
-        rc = replay(1, h.mean, &t);
-        if (rc != NL_OK) return rc;
+        const int proven = force_replay ? 0 : prove(1, h.mean, h, &t);
+        if (proven < 0) return cuda_fail(cudaGetLastError(), "second-level proof");
+        if (proven) {
+            for (int i = 0; i < n_tail; i++) { volatile float d = tail[i] - h.mean; const double dd = (double)d; volatile double sq = dd * dd; t += sq; }
+        } else {
+            rc = replay(1, h.mean, &t);
+            if (rc != NL_OK) return rc;
+        }
         h.stddev = (float)sqrt(t / dn);
     }
     out[0] = h.mn; out[1] = h.mean; out[2] = h.mx; out[3] = h.stddev;

@@ -44,17 +44,26 @@ __device__ __forceinline__ float project_pixel(const float *__restrict__ src, in
 // destination pixels of a row, so every one of the 16 gathers of a thread is a (nearly) contiguous
 // 128-byte warp access and every store a full 128-byte line; the four rows give each thread 16
 // independent loads in flight and their 2x2 footprints share L1 lines with the rows above and below.
+#ifndef NL_PROJ_ROWS
+#define NL_PROJ_ROWS 4
+#endif
+#ifndef NL_PROJ_BX
+#define NL_PROJ_BX 64
+#endif
+constexpr int PR = NL_PROJ_ROWS;          // destination rows per thread
+constexpr int PBX = NL_PROJ_BX, PBY = 256 / NL_PROJ_BX;
+
 template <bool SCALE>
 __global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ src, int sw, int sh, float *__restrict__ dst,
                                                       int dw, int dh, Affine inv, float oob, float mult, float offset) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
+    const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * PR;
     if (col >= dw || row0 >= dh) return;
-    float v[4];
+    float v[PR];
 #pragma unroll
-    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, col, row0 + r, oob, mult, offset) : 0.0f;
+    for (int r = 0; r < PR; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, col, row0 + r, oob, mult, offset) : 0.0f;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int r = 0; r < PR; r++)
         if (row0 + r < dh) __stcs(dst + (size_t)(row0 + r) * dw + col, v[r]);
 }
 
@@ -124,8 +133,8 @@ static int project_launch(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t
     NL_REQUIRE(dev_dst && (dev_src || sw == 0 || sh == 0), "NULL image pointer");
     CtxGuard g(ctx);
     Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
-    dim3 block(64, 4);
-    dim3 grid((dw + block.x - 1) / block.x, (dh + 4 * block.y - 1) / (4 * block.y));
+    dim3 block(PBX, PBY);
+    dim3 grid((dw + block.x - 1) / block.x, (dh + PR * block.y - 1) / (PR * block.y));
     if (scale) project_kernel<true><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob, mult, offset);
     else project_kernel<false><<<grid, block, 0, ctx->stream>>>(dev_src, sw, sh, dev_dst, dw, dh, a, oob, 1.0f, 0.0f);
     NL_CUDA(cudaGetLastError());

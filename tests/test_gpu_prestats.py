@@ -77,20 +77,37 @@ def test_stats_signed_zero_and_nan_extremes(ctx, numerics):
         assert np.isnan(got[[0, 2]]).tolist() == np.isnan(want[[0, 2]]).tolist()
 
 
-def test_stats_near_rounding_boundaries_take_the_exact_replay(ctx):
-    """Data built so that the float64 sum sits on a float32 rounding boundary of the mean: the interval test
-    cannot decide, the chains are replayed in order, and the result still equals the oracle's bit for bit"""
+def _steered_to_a_mean_boundary(rng, n, tiny):
+    """data whose float64 sum sits (within the rounding of one element) on the midpoint between two float32 means"""
+    data = (rng.standard_normal(n) * 3 + 50).astype(np.float32)
+    if tiny:
+        k = rng.integers(1, n, size=n // 50)
+        data[k] = (rng.standard_normal(k.size) * 1e-9).astype(np.float32)      # terms far below the accumulator's ulp
+    s = float(np.sum(data.astype(np.float64)))
+    m = np.float32(s / n)
+    mid = (float(m) + float(np.nextafter(m, np.float32(np.inf)))) / 2
+    data[0] = np.float32(float(data[0]) + (mid * n - s))
+    return data
+
+
+def test_stats_on_a_rounding_boundary_proven_without_replay(ctx):
+    """The first-level interval cannot decide a sum that sits on a float32 rounding boundary of the mean; when no term
+    can round at all (every term a multiple of the accumulator's ulp) the second-level proof settles it exactly."""
     ctx.set_numerics(nl.NUMERICS_AMD64)
     before = ctx.exact_replays()
-    n = 1 << 16
     for seed in range(6):
-        rng = np.random.default_rng(100 + seed)
-        data = (rng.standard_normal(n) * 3 + 50).astype(np.float32)
-        # steer the sum onto the midpoint between two neighbouring float32 means
-        s = float(np.sum(data.astype(np.float64)))
-        m = np.float32(s / n)
-        mid = (float(m) + float(np.nextafter(m, np.float32(np.inf)))) / 2
-        data[0] = np.float32(float(data[0]) + (mid * n - s))
+        data = _steered_to_a_mean_boundary(np.random.default_rng(100 + seed), 1 << 16, tiny=False)
+        got, want = nl.stats(ctx, data), O.stats(data, amd64=True)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (seed, got, want)
+    assert ctx.exact_replays() == before
+
+
+def test_stats_near_rounding_boundaries_take_the_exact_replay(ctx):
+    """...and when many terms do round, the chains are replayed in order; the result still equals the oracle's bit for bit"""
+    ctx.set_numerics(nl.NUMERICS_AMD64)
+    before = ctx.exact_replays()
+    for seed in range(6):
+        data = _steered_to_a_mean_boundary(np.random.default_rng(200 + seed), 1 << 16, tiny=True)
         got, want = nl.stats(ctx, data), O.stats(data, amd64=True)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (seed, got, want)
     assert ctx.exact_replays() > before

@@ -4,8 +4,8 @@
     python tools/bench_kernels.py [--quick]
 
 One JSON line per kernel: achieved = ALGORITHMIC bytes per launch / CUDA-event time (DESIGN.md section 3
-states the per-unit figures), peak = MEASURED_PEAKS.json hbm_gbs.  Inputs are larger than L2 (126 MB) or
-the L2 is flushed between launches.  bench.py remains the headline benchmark; this is the per-kernel view
+states the per-unit figures), peak = MEASURED_PEAKS.json hbm_gbs.  Inputs are larger than L2 (126 MB): the stack
+jobs by themselves, the per-frame kernels by rotating through distinct frames (steady state, no flush).  bench.py remains the headline benchmark; this is the per-kernel view
 the ncu captures under profiles/ are taken from.
 """
 import argparse
@@ -58,6 +58,26 @@ def main():
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
         return float(np.median(ms))
+
+    def timed_rot(fns, rounds=3):
+        """Steady state over a rotation of distinct frames whose total size exceeds L2 (no flush: a flush by writing
+        leaves 126 MB of dirty lines whose write-back would be charged to a 30-microsecond kernel).  Average per call."""
+        for f in fns:
+            f()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        for _ in range(rounds):
+            for f in fns:
+                f()
+        with torch.cuda.stream(ext):
+            e1.record()
+        ctx.sync()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (rounds * len(fns))
+
+    ROT = 6            # frames in rotation: 6 x (96 MB in + 96 MB out) at 6000x4000
 
     def report(kernel, workload, algo_bytes, ms, extra=None):
         ach = algo_bytes / (ms * 1e-3) / 1e9
@@ -112,92 +132,89 @@ def main():
         del out
 
     # ---- resample: 6000x4000 -> 6000x4000, rotation 0.5 deg + shift ---------------------------------
-    if not only or "project" in only:
+    if not only or "project" in only or "fits" in only:
         w, h = (3000, 2000) if args.quick else (6000, 4000)
-        src = torch.empty(w * h, dtype=torch.float32, device=dev)
-        dst = torch.empty(w * h, dtype=torch.float32, device=dev)
-        ctx.synth_fill(src.data_ptr(), 0, w * h, 0)
+        srcs = [torch.empty(w * h, dtype=torch.float32, device=dev) for _ in range(ROT)]
+        dsts = [torch.empty(w * h, dtype=torch.float32, device=dev) for _ in range(ROT)]
+        for k, t in enumerate(srcs):
+            ctx.synth_fill(t.data_ptr(), 0, w * h, k)
         th = np.deg2rad(0.5)
         trans = (C.c_float * 6)(np.cos(th), -np.sin(th), 7.25, np.sin(th), np.cos(th), -3.5)
-        ms = timed(lambda: nl.binding.check(lib.nl_project_dev(ctx.handle, C.c_void_p(src.data_ptr()), w, h, C.c_void_p(dst.data_ptr()),
-                                                               w, h, trans, float("nan"))))
-        report("project_kernel", "%dx%d -> %dx%d, rot 0.5 deg + shift, L2 flushed" % (w, h, w, h), 8.0 * w * h, ms,
-               {"mpx_per_s": w * h / ms / 1e3})
-        del src, dst
+        rot = "%d frames of %dx%d in rotation (%.1f GB > L2), no flush" % (ROT, w, h, ROT * 8.0 * w * h / 1e9)
+        if not only or "project" in only:
+            ms = timed_rot([lambda a=a, b=b: nl.binding.check(lib.nl_project_dev(ctx.handle, C.c_void_p(a.data_ptr()), w, h, C.c_void_p(b.data_ptr()),
+                                                                                 w, h, trans, float("nan"))) for a, b in zip(srcs, dsts)])
+            report("project_kernel", "rot 0.5 deg + shift; " + rot, 8.0 * w * h, ms, {"mpx_per_s": w * h / ms / 1e3})
+        # ---- N1: resample fused with the histogram match, FITS payload decode (16-bit) and encode ---------
+        if not only or "fits" in only:
+            ms = timed_rot([lambda a=a, b=b: nl.binding.check(lib.nl_project_scaled_dev(ctx.handle, C.c_void_p(a.data_ptr()), w, h,
+                                                                                        C.c_void_p(b.data_ptr()), w, h, trans, float("nan"), 1.03, -5.0))
+                            for a, b in zip(srcs, dsts)])
+            report("project_kernel<scaled> (match histogram fused)", rot, 8.0 * w * h, ms)
+            raws = [torch.randint(-32768, 32767, (w * h,), dtype=torch.int16, device=dev) for _ in range(2 * ROT)]
+            ms = timed_rot([lambda r=r, b=dsts[i % ROT]: nl.binding.check(lib.nl_fits_decode_dev(ctx.handle, C.c_void_p(r.data_ptr()), 16, w * h, 1.0, 32768.0,
+                                                                                                  C.c_void_p(b.data_ptr()))) for i, r in enumerate(raws)])
+            report("fits_decode_kernel<16>", "%d frames of %d samples in rotation, no flush" % (2 * ROT, w * h), 6.0 * w * h, ms)
+            ms = timed_rot([lambda a=a, b=b: nl.binding.check(lib.nl_fits_encode_dev(ctx.handle, C.c_void_p(a.data_ptr()), w * h, C.c_void_p(b.data_ptr())))
+                            for a, b in zip(srcs, dsts)])
+            report("fits_encode_kernel", rot, 8.0 * w * h, ms)
+            del raws
+        del srcs, dsts
 
-    # ---- N1: resample fused with the histogram match, FITS payload decode (16-bit) and encode ---------
-    if not only or "fits" in only:
+    # ---- star candidate scan and frame statistics: 6000x4000 sky noise + 0.02 % bright pixels, frames in rotation ----
+    if not only or "bright" in only or "prestats" in only:
         w, h = (3000, 2000) if args.quick else (6000, 4000)
-        src = torch.empty(w * h, dtype=torch.float32, device=dev)
-        dst = torch.empty(w * h, dtype=torch.float32, device=dev)
-        ctx.synth_fill(src.data_ptr(), 0, w * h, 0)
-        th = np.deg2rad(0.5)
-        trans = (C.c_float * 6)(np.cos(th), -np.sin(th), 7.25, np.sin(th), np.cos(th), -3.5)
-        ms = timed(lambda: nl.binding.check(lib.nl_project_scaled_dev(ctx.handle, C.c_void_p(src.data_ptr()), w, h, C.c_void_p(dst.data_ptr()),
-                                                                      w, h, trans, float("nan"), 1.03, -5.0)))
-        report("project_kernel<scaled> (match histogram fused)", "%dx%d, L2 flushed" % (w, h), 8.0 * w * h, ms)
-        raw = torch.randint(-32768, 32767, (w * h,), dtype=torch.int16, device=dev)
-        ms = timed(lambda: nl.binding.check(lib.nl_fits_decode_dev(ctx.handle, C.c_void_p(raw.data_ptr()), 16, w * h, 1.0, 32768.0,
-                                                                   C.c_void_p(dst.data_ptr()))))
-        report("fits_decode_kernel<16>", "%d samples, L2 flushed" % (w * h), 6.0 * w * h, ms)
-        ms = timed(lambda: nl.binding.check(lib.nl_fits_encode_dev(ctx.handle, C.c_void_p(src.data_ptr()), w * h, C.c_void_p(dst.data_ptr()))))
-        report("fits_encode_kernel", "%d samples, L2 flushed" % (w * h), 8.0 * w * h, ms)
-        del src, dst, raw
-
-    # ---- star candidate scan: 6000x4000 sky noise + 0.02 % bright pixels --------------------------------
-    if not only or "bright" in only:
-        w, h = (3000, 2000) if args.quick else (6000, 4000)
-        # sky noise around 1000 with 0.02 % bright "star" pixels
         g = torch.Generator(device=dev).manual_seed(7)
-        img = torch.randn(w * h, dtype=torch.float32, device=dev, generator=g) * 30 + 1000
-        img += (torch.rand(w * h, device=dev, generator=g) < 2e-4).float() * 5000
-        cap = w * h // 50
-        out = np.zeros(cap, dtype=nl.STAR_DTYPE)
-        cnt = C.c_int32()
-        ms = timed(lambda: nl.binding.check(lib.nl_find_bright_dev(ctx.handle, C.c_void_p(img.data_ptr()), w * h, w, 3000.0, 16,
-                                                                   out.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))))
-        report("find_bright (2 scans + offsets + D2H of candidates)", "%dx%d, radius 16, %d candidates, L2 flushed" % (w, h, cnt.value),
-               4.0 * w * h, ms, {"mpx_per_s": w * h / ms / 1e3, "note": "whole call incl. host sync; the image is read twice (count, write)"})
-        del img
-
-    # ---- N2 / N3: frame statistics (noise estimate, 3x3 median filter, min/mean/max/stddev, bad-pixel map) ----
-    if not only or "prestats" in only:
-        w, h = (3000, 2000) if args.quick else (6000, 4000)
-        g = torch.Generator(device=dev).manual_seed(11)
-        img = torch.randn(w * h, dtype=torch.float32, device=dev, generator=g) * 30 + 1000
-        img += (torch.rand(w * h, device=dev, generator=g) < 2e-4).float() * 5000
-        tmp = torch.empty_like(img)
-        st = (C.c_float * 4)()
-        one = (C.c_float * 1)()
-        for numerics, tag in ((nl.NUMERICS_AMD64, "amd64"), (nl.NUMERICS_PUREGO, "purego")):
-            ctx.set_numerics(numerics)
-            ms = timed(lambda: nl.binding.check(lib.nl_estimate_noise_dev(ctx.handle, C.c_void_p(img.data_ptr()), 1, w * h, w, h, one)))
-            report("estimate_noise (%s order; rows kernel + finalize + D2H)" % tag, "%dx%d, L2 flushed" % (w, h), 4.0 * w * h, ms)
-            ms = timed(lambda: nl.binding.check(lib.nl_median_filter3x3_dev(ctx.handle, C.c_void_p(img.data_ptr()), w, h, C.c_void_p(tmp.data_ptr()))))
-            report("median3x3_kernel (%s)" % tag, "%dx%d, L2 flushed" % (w, h), 8.0 * w * h, ms)
-            r0 = ctx.exact_replays()
-            ms = timed(lambda: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(tmp.data_ptr()), w * h, st)))
-            report("stats min/mean/max/stddev (%s; 2 fused passes, one read-back)" % tag, "%dx%d, L2 flushed" % (w, h), 8.0 * w * h, ms,
-                   {"exact_replays": ctx.exact_replays() - r0})
+        imgs = []
+        for k in range(2 * ROT):
+            img = torch.randn(w * h, dtype=torch.float32, device=dev, generator=g) * 30 + 1000
+            img += (torch.rand(w * h, device=dev, generator=g) < 2e-4).float() * 5000
+            imgs.append(img)
+        tmps = [torch.empty(w * h, dtype=torch.float32, device=dev) for _ in range(ROT)]
+        rot = "%d frames of %dx%d in rotation (%.1f GB > L2), no flush" % (2 * ROT, w, h, 2 * ROT * 4.0 * w * h / 1e9)
+        if not only or "bright" in only:
             cap = w * h // 50
-            bpm = np.empty(cap, dtype=np.int32)
-            cnt = C.c_int64()
-            ms = timed(lambda: nl.binding.check(lib.nl_bad_pixel_map_dev(ctx.handle, C.c_void_p(img.data_ptr()), w * h, w, 3.0, 5.0,
-                                                                         C.c_void_p(tmp.data_ptr()), bpm.ctypes.data_as(C.POINTER(C.c_int32)),
-                                                                         cap, C.byref(cnt), st)))
-            report("bad_pixel_map whole call (%s; median-diff, stats, 2 scans)" % tag, "%dx%d, %d bad pixels, L2 flushed" % (w, h, cnt.value),
-                   24.0 * w * h, ms)
-        ctx.set_numerics(nl.NUMERICS_AMD64)
-        # the in-order replay of the float64 chains (taken when the interval test cannot decide): force it with a NaN-free
-        # frame whose sum is steered onto a rounding boundary is data-dependent, so time the kernel through its worst case:
-        # a frame containing one NaN makes every interval test fail
-        img2 = img.clone()
-        img2[12345] = float("nan")
-        r0 = ctx.exact_replays()
-        ms = timed(lambda: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(img2.data_ptr()), w * h, st)), reps=3, warm=1)
-        report("stats with both chains replayed in order (worst case)", "%dx%d" % (w, h), 8.0 * w * h, ms,
-               {"exact_replays": ctx.exact_replays() - r0})
-        del img, tmp, img2
+            out = np.zeros(cap, dtype=nl.STAR_DTYPE)
+            cnt = C.c_int32()
+            ms = timed_rot([lambda im=im: nl.binding.check(lib.nl_find_bright_dev(ctx.handle, C.c_void_p(im.data_ptr()), w * h, w, 3000.0, 16,
+                                                                                  out.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))) for im in imgs])
+            report("find_bright (2 scans + offsets + D2H of candidates)", "radius 16, %d candidates; %s" % (cnt.value, rot),
+                   4.0 * w * h, ms, {"mpx_per_s": w * h / ms / 1e3, "note": "whole call incl. host sync; the image is read twice (count, write)"})
+        if not only or "prestats" in only:
+            st = (C.c_float * 4)()
+            one = (C.c_float * 1)()
+            for numerics, tag in ((nl.NUMERICS_AMD64, "amd64"), (nl.NUMERICS_PUREGO, "purego")):
+                ctx.set_numerics(numerics)
+                ms = timed_rot([lambda im=im: nl.binding.check(lib.nl_estimate_noise_dev(ctx.handle, C.c_void_p(im.data_ptr()), 1, w * h, w, h, one))
+                                for im in imgs])
+                report("estimate_noise (%s order; rows kernel + finalize + D2H)" % tag, rot, 4.0 * w * h, ms)
+                ms = timed_rot([lambda im=im, t=tmps[i % ROT]: nl.binding.check(lib.nl_median_filter3x3_dev(ctx.handle, C.c_void_p(im.data_ptr()), w, h,
+                                                                                                             C.c_void_p(t.data_ptr()))) for i, im in enumerate(imgs)])
+                report("median3x3_kernel (%s)" % tag, rot, 8.0 * w * h, ms)
+                r0 = ctx.exact_replays()
+                ms = timed_rot([lambda im=im: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(im.data_ptr()), w * h, st)) for im in imgs])
+                report("stats min/mean/max/stddev (%s; 2 fused passes, one read-back)" % tag, rot, 8.0 * w * h, ms,
+                       {"exact_replays": ctx.exact_replays() - r0})
+                cap = w * h // 50
+                bpm = np.empty(cap, dtype=np.int32)
+                cnt = C.c_int64()
+                r0 = ctx.exact_replays()
+                ms = timed_rot([lambda im=im, t=tmps[i % ROT]: nl.binding.check(lib.nl_bad_pixel_map_dev(
+                    ctx.handle, C.c_void_p(im.data_ptr()), w * h, w, 3.0, 5.0, C.c_void_p(t.data_ptr()), bpm.ctypes.data_as(C.POINTER(C.c_int32)),
+                    cap, C.byref(cnt), st)) for i, im in enumerate(imgs)])
+                report("bad_pixel_map whole call (%s; median-diff, stats, 2 scans)" % tag, "%d bad pixels; %s" % (cnt.value, rot),
+                       24.0 * w * h, ms, {"exact_replays": ctx.exact_replays() - r0})
+            ctx.set_numerics(nl.NUMERICS_AMD64)
+            # the in-order replay of the float64 chains (taken when neither proof decides), forced for the measurement
+            img2 = imgs[0]
+            os.environ["NL_STATS_FORCE_REPLAY"] = "1"
+            r0 = ctx.exact_replays()
+            ms = timed(lambda: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(img2.data_ptr()), w * h, st)), reps=3, warm=1)
+            os.environ.pop("NL_STATS_FORCE_REPLAY")
+            report("stats with both chains replayed in order (worst case)", "%dx%d" % (w, h), 8.0 * w * h, ms,
+                   {"exact_replays": ctx.exact_replays() - r0})
+            del img2
+        del imgs, tmps
 
     # ---- stack-of-stacks accumulate -----------------------------------------------------------------
     if not only or "incremental" in only:
