@@ -296,7 +296,7 @@ def run_b200(args):
         except Exception:
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "stack_column_kernel<sigma>", "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": "stack_column_kernel<sigma> (per step: one launch over the frame stack + one over the pool of columns whose late clipping passes were deferred)", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src}
 
     # ---- end to end through the C ABI with host buffers (rank-local; max over ranks)
