@@ -413,11 +413,47 @@ int nl_stack_end(nl_stack_job *job) {
 }
 
 // StackIncremental / StackIncrementalFinalize, stack.go:924-944
+// four pixels per thread and iteration (float4) when both buffers are 16-byte aligned, two iterations in flight
+__global__ void __launch_bounds__(256) incremental_vec_kernel(float *__restrict__ acc, const float *__restrict__ light, long long n,
+                                                              float w, int first) {
+    const long long n4 = n >> 2, step = (long long)gridDim.x * blockDim.x;
+    float4 *a4 = reinterpret_cast<float4 *>(acc);
+    const float4 *l4 = reinterpret_cast<const float4 *>(light);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += 2 * step) {
+        const bool two = i + step < n4;
+        const float4 x0 = __ldcs(l4 + i), x1 = two ? __ldcs(l4 + i + step) : make_float4(0, 0, 0, 0);
+        float4 y0 = make_float4(0, 0, 0, 0), y1 = y0;
+        if (!first) { y0 = a4[i]; if (two) y1 = a4[i + step]; }
+        float4 r0, r1;
+        r0.x = __fmul_rn(x0.x, w); r0.y = __fmul_rn(x0.y, w); r0.z = __fmul_rn(x0.z, w); r0.w = __fmul_rn(x0.w, w);
+        r1.x = __fmul_rn(x1.x, w); r1.y = __fmul_rn(x1.y, w); r1.z = __fmul_rn(x1.z, w); r1.w = __fmul_rn(x1.w, w);
+        if (!first) {
+            r0.x = __fadd_rn(y0.x, r0.x); r0.y = __fadd_rn(y0.y, r0.y); r0.z = __fadd_rn(y0.z, r0.z); r0.w = __fadd_rn(y0.w, r0.w);
+            r1.x = __fadd_rn(y1.x, r1.x); r1.y = __fadd_rn(y1.y, r1.y); r1.z = __fadd_rn(y1.z, r1.z); r1.w = __fadd_rn(y1.w, r1.w);
+        }
+        a4[i] = r0;
+        if (two) a4[i + step] = r1;
+    }
+    // the up-to-three pixels behind the last whole float4
+    const long long t = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) { const float v = __fmul_rn(light[t], w); acc[t] = first ? v : __fadd_rn(acc[t], v); }
+}
 __global__ void incremental_kernel(float *acc, const float *light, long long n, float w, int first) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float t = __fmul_rn(light[i], w);
         acc[i] = first ? t : __fadd_rn(acc[i], t);
     }
+}
+__global__ void __launch_bounds__(256) scale_vec_kernel(float *__restrict__ acc, long long n, float factor) {
+    const long long n4 = n >> 2;
+    float4 *a4 = reinterpret_cast<float4 *>(acc);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = a4[i];
+        v.x = __fmul_rn(v.x, factor); v.y = __fmul_rn(v.y, factor); v.z = __fmul_rn(v.z, factor); v.w = __fmul_rn(v.w, factor);
+        a4[i] = v;
+    }
+    const long long t = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) acc[t] = __fmul_rn(acc[t], factor);
 }
 __global__ void scale_kernel(float *acc, long long n, float factor) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -429,9 +465,12 @@ int nl_stack_incremental_dev(nl_ctx *ctx, float *dev_acc, const float *dev_light
     if (pixels == 0) return NL_OK;
     NL_REQUIRE(dev_acc && dev_light, "NULL argument");
     CtxGuard g(ctx);
-    long long grid = (pixels + 255) / 256;
-    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
-    incremental_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, dev_light, pixels, weight, first);
+    const bool vec = (((uintptr_t)dev_acc | (uintptr_t)dev_light) & 15) == 0;
+    long long grid = ((vec ? pixels / 8 : pixels) + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 8) grid = (long long)ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    if (vec) incremental_vec_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, dev_light, pixels, weight, first);
+    else incremental_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, dev_light, pixels, weight, first);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;
@@ -443,9 +482,12 @@ int nl_stack_incremental_finalize_dev(nl_ctx *ctx, float *dev_acc, int64_t pixel
     NL_REQUIRE(dev_acc, "NULL argument");
     CtxGuard g(ctx);
     float factor = 1.0f / weight_sum;    // stack.go:941
-    long long grid = (pixels + 255) / 256;
-    if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
-    scale_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, pixels, factor);
+    const bool vec = ((uintptr_t)dev_acc & 15) == 0;
+    long long grid = ((vec ? pixels / 4 : pixels) + 255) / 256;
+    if (grid > (long long)ctx->sm_count * 8) grid = (long long)ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    if (vec) scale_vec_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, pixels, factor);
+    else scale_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_acc, pixels, factor);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     return NL_OK;

@@ -347,3 +347,31 @@ def test_default_deferral_schedules_on_the_synthetic_workload(ctx):
     frames = O.synth_frames(128, 4096 * 100, 32 * 300)
     for mode, weighted in (("sigma", False), ("winsor", True), ("linfit", False)):
         check_against_oracle(ctx, frames, mode, weighted)
+
+
+@pytest.mark.parametrize("pixels,offset", [(1, 0), (3, 0), (4, 0), (1000003, 0), (4099, 1), (65536, 3)])
+def test_incremental_kernels_vector_and_scalar_paths(ctx, pixels, offset):
+    """StackIncremental / StackIncrementalFinalize (stack.go:924-944): acc = light*w, acc += light*w (mul then add),
+    acc *= 1/weightSum -- float4 path for 16-byte aligned buffers, scalar path otherwise, ragged tails"""
+    import ctypes as C
+    from nightlight_b200.binding import check, load_library
+    lib = load_library()
+    rng = np.random.default_rng(pixels + offset)
+    a = (rng.standard_normal(pixels) * 50 + 10).astype(np.float32)
+    b = (rng.standard_normal(pixels) * 50 + 10).astype(np.float32)
+    dev = ctx.dev_alloc(4 * (2 * pixels + 64))
+    try:
+        acc, light = dev + 4 * offset, dev + 4 * (pixels + 16 + offset) + (0 if offset == 0 else 4 * ((4 - (pixels + offset) % 4) % 4))
+        ctx.h2d(light, a)
+        check(lib.nl_stack_incremental_dev(ctx.handle, C.c_void_p(acc), C.c_void_p(light), pixels, 3.0, 1))
+        ctx.h2d(light, b)
+        check(lib.nl_stack_incremental_dev(ctx.handle, C.c_void_p(acc), C.c_void_p(light), pixels, 5.0, 0))
+        check(lib.nl_stack_incremental_finalize_dev(ctx.handle, C.c_void_p(acc), pixels, 8.0))
+        got = np.empty(pixels, np.float32)
+        ctx.d2h(got, acc)
+        want = (a * np.float32(3.0)).astype(np.float32)
+        want = (want + (b * np.float32(5.0)).astype(np.float32)).astype(np.float32)
+        want = (want * (np.float32(1.0) / np.float32(8.0))).astype(np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    finally:
+        ctx.dev_free(dev)
