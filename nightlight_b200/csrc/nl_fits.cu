@@ -33,6 +33,56 @@ __global__ void __launch_bounds__(256) fits_decode_kernel(const unsigned char *_
         dst[i] = __fadd_rn(__fmul_rn(fits_value<BITPIX>(raw, i), bscale), bzero);     // read.go:196, 237, ...
 }
 
+// Four samples per thread for the two payload types that matter (16-bit camera frames, fp32 stacks): one 8- or 16-byte
+// load and one 16-byte store; the up-to-three samples behind the last whole group take the scalar form.
+template <int BITPIX>
+__global__ void __launch_bounds__(256) fits_decode_vec_kernel(const unsigned char *__restrict__ raw, long long n, float bscale,
+                                                              float bzero, float *__restrict__ dst) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float v[4];
+        if (BITPIX == 16) {
+            const uint2 u = __ldcs(reinterpret_cast<const uint2 *>(raw) + i);
+            const unsigned w[2] = {u.x, u.y};
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const unsigned lo = w[k] & 0xffffu, hi = w[k] >> 16;
+                v[2 * k] = (float)(short)(unsigned short)(((lo << 8) | (lo >> 8)) & 0xffffu);
+                v[2 * k + 1] = (float)(short)(unsigned short)(((hi << 8) | (hi >> 8)) & 0xffffu);
+            }
+        } else {
+            const uint4 u = __ldcs(reinterpret_cast<const uint4 *>(raw) + i);
+            v[0] = __uint_as_float(bswap32(u.x)); v[1] = __uint_as_float(bswap32(u.y));
+            v[2] = __uint_as_float(bswap32(u.z)); v[3] = __uint_as_float(bswap32(u.w));
+        }
+        float4 o;
+        o.x = __fadd_rn(__fmul_rn(v[0], bscale), bzero); o.y = __fadd_rn(__fmul_rn(v[1], bscale), bzero);
+        o.z = __fadd_rn(__fmul_rn(v[2], bscale), bzero); o.w = __fadd_rn(__fmul_rn(v[3], bscale), bzero);
+        reinterpret_cast<float4 *>(dst)[i] = o;
+    }
+    const long long t = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = __fadd_rn(__fmul_rn(fits_value<BITPIX>(raw, t), bscale), bzero);
+}
+
+__global__ void __launch_bounds__(256) fits_encode_vec_kernel(const float *__restrict__ src, long long n, unsigned *__restrict__ raw) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 d = __ldcs(reinterpret_cast<const float4 *>(src) + i);
+        if (d.x != d.x) d.x = 0.0f;                                    // write.go:192
+        if (d.y != d.y) d.y = 0.0f;
+        if (d.z != d.z) d.z = 0.0f;
+        if (d.w != d.w) d.w = 0.0f;
+        reinterpret_cast<uint4 *>(raw)[i] = make_uint4(bswap32(__float_as_uint(d.x)), bswap32(__float_as_uint(d.y)),
+                                                       bswap32(__float_as_uint(d.z)), bswap32(__float_as_uint(d.w)));
+    }
+    const long long t = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) {
+        float d = src[t];
+        if (d != d) d = 0.0f;
+        raw[t] = bswap32(__float_as_uint(d));
+    }
+}
+
 __global__ void __launch_bounds__(256) fits_encode_kernel(const float *__restrict__ src, long long n, unsigned *__restrict__ raw) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float d = src[i];
@@ -46,6 +96,16 @@ int fits_decode_launch(nl_ctx *ctx, const void *dev_raw, int bitpix, long long n
     long long grid = (n + 255) / 256;
     if (grid > (long long)ctx->sm_count * 32) grid = (long long)ctx->sm_count * 32;
     const unsigned char *raw = (const unsigned char *)dev_raw;
+    if ((bitpix == 16 || bitpix == -32) && (((uintptr_t)dev_raw | (uintptr_t)dev_dst) & 15) == 0) {
+        long long vgrid = (n / 4 + 255) / 256;
+        if (vgrid > (long long)ctx->sm_count * 16) vgrid = (long long)ctx->sm_count * 16;
+        if (vgrid < 1) vgrid = 1;
+        if (bitpix == 16) fits_decode_vec_kernel<16><<<(unsigned)vgrid, 256, 0, ctx->stream>>>(raw, n, bscale, bzero, dev_dst);
+        else fits_decode_vec_kernel<-32><<<(unsigned)vgrid, 256, 0, ctx->stream>>>(raw, n, bscale, bzero, dev_dst);
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return NL_OK;
+    }
     switch (bitpix) {
     case 8: fits_decode_kernel<8><<<(unsigned)grid, 256, 0, ctx->stream>>>(raw, n, bscale, bzero, dev_dst); break;
     case 16: fits_decode_kernel<16><<<(unsigned)grid, 256, 0, ctx->stream>>>(raw, n, bscale, bzero, dev_dst); break;
@@ -94,6 +154,15 @@ int nl_fits_encode_dev(nl_ctx *ctx, const float *dev_src, int64_t count, void *d
     NL_REQUIRE(ctx && count >= 0 && (count == 0 || (dev_src && dev_raw)), "bad argument");
     if (count == 0) return NL_OK;
     CtxGuard g(ctx);
+    if ((((uintptr_t)dev_src | (uintptr_t)dev_raw) & 15) == 0) {
+        long long vgrid = (count / 4 + 255) / 256;
+        if (vgrid > (long long)ctx->sm_count * 16) vgrid = (long long)ctx->sm_count * 16;
+        if (vgrid < 1) vgrid = 1;
+        fits_encode_vec_kernel<<<(unsigned)vgrid, 256, 0, ctx->stream>>>(dev_src, count, (unsigned *)dev_raw);
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return NL_OK;
+    }
     long long grid = (count + 255) / 256;
     if (grid > (long long)ctx->sm_count * 32) grid = (long long)ctx->sm_count * 32;
     fits_encode_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_src, count, (unsigned *)dev_raw);
