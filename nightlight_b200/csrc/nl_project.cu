@@ -14,19 +14,20 @@ struct Affine { float a, b, c, d, e, f; };
 // SCALE: every gathered source sample first becomes d*mult + offset (mul, then add), i.e. the result is
 // that of Image.MatchHistogram (internal/fits/pixelops.go:601-612) followed by Project, in one pass.
 template <bool SCALE>
-__device__ __forceinline__ float project_pixel(const float *__restrict__ src, int sw, int sh, const Affine &inv, int col,
+__device__ __forceinline__ float project_pixel(const float *__restrict__ src, int sw, int sh, const Affine &inv, float ax, float dx,
                                                int row, float oob, float mult, float offset) {
-    const float x = (float)col, y = (float)row;
+    // ax = A*x and dx = D*x are the same for every row of a thread's column (the products round once either way)
+    const float y = (float)row;
     // coord.go:141-145: (A*x + B*y) + C
-    const float px = __fadd_rn(__fadd_rn(__fmul_rn(inv.a, x), __fmul_rn(inv.b, y)), inv.c);
-    const float py = __fadd_rn(__fadd_rn(__fmul_rn(inv.d, x), __fmul_rn(inv.e, y)), inv.f);
+    const float px = __fadd_rn(__fadd_rn(ax, __fmul_rn(inv.b, y)), inv.c);
+    const float py = __fadd_rn(__fadd_rn(dx, __fmul_rn(inv.e, y)), inv.f);
     const float fx = floorf(px), fy = floorf(py);
     float v = oob;
     // project.go:49-61; the float comparison form also rejects NaN and out-of-int32 coordinates
     if (fx >= 0.0f && fy >= 0.0f && fx < (float)(sw - 1) && fy < (float)(sh - 1)) {
         const int xl = (int)fx, yl = (int)fy;
         const float xr = __fsub_rn(px, fx), yr = __fsub_rn(py, fy);
-        const float *s = src + (size_t)yl * sw + xl;
+        const float *s = src + ((unsigned)yl * (unsigned)sw + (unsigned)xl);     // (pixel counts are int32 in the reference)
         float d00 = __ldg(s), d10 = __ldg(s + 1), d01 = __ldg(s + sw), d11 = __ldg(s + sw + 1);
         if (SCALE) {
             d00 = __fadd_rn(__fmul_rn(d00, mult), offset); d10 = __fadd_rn(__fmul_rn(d10, mult), offset);
@@ -59,9 +60,10 @@ __global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ 
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * PR;
     if (col >= dw || row0 >= dh) return;
+    const float x = (float)col, ax = __fmul_rn(inv.a, x), dx = __fmul_rn(inv.d, x);
     float v[PR];
 #pragma unroll
-    for (int r = 0; r < PR; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, col, row0 + r, oob, mult, offset) : 0.0f;
+    for (int r = 0; r < PR; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, ax, dx, row0 + r, oob, mult, offset) : 0.0f;
 #pragma unroll
     for (int r = 0; r < PR; r++)
         if (row0 + r < dh) __stcs(dst + (size_t)(row0 + r) * dw + col, v[r]);
@@ -83,9 +85,10 @@ __global__ void __launch_bounds__(256) project_scatter_kernel(const float *__res
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
     if (col >= dw || row0 >= dh) return;
+    const float x = (float)col, ax = __fmul_rn(inv.a, x), dx = __fmul_rn(inv.d, x);
     float v[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, col, row0 + r, oob, mult, offset) : 0.0f;
+    for (int r = 0; r < 4; r++) v[r] = (row0 + r < dh) ? project_pixel<SCALE>(src, sw, sh, inv, ax, dx, row0 + r, oob, mult, offset) : 0.0f;
     int g = 0;
     while (g + 1 < sc.n && row0 >= sc.row0[g + 1]) g++;
 #pragma unroll
@@ -126,6 +129,7 @@ static int project_launch(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t
                           const float trans[6], float oob, bool scale, float mult, float offset) {
     NL_REQUIRE(ctx && trans, "NULL argument");
     NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0, "negative image size");
+    NL_REQUIRE((long long)sw * sh <= 0x7fffffffll && (long long)dw * dh <= 0x7fffffffll, "image larger than int32 pixels (fits.go:40)");
     float inv[6];
     int rc = nl_transform_invert(trans, inv);
     if (rc != NL_OK) return rc;
@@ -157,6 +161,7 @@ int nl_project_scatter_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_
                            const int32_t *stripe_row0, int32_t n_stripes) {
     NL_REQUIRE(ctx && trans && stripe_frames && stripe_row0, "NULL argument");
     NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0 && frame_index >= 0, "negative size or index");
+    NL_REQUIRE((long long)sw * sh <= 0x7fffffffll && (long long)dw * dh <= 0x7fffffffll, "image larger than int32 pixels (fits.go:40)");
     NL_REQUIRE(n_stripes >= 1 && n_stripes <= NL_MAX_PEERS, "stripe count out of range");
     NL_REQUIRE(stripe_row0[0] == 0 && stripe_row0[n_stripes] == dh, "stripes must cover rows [0, dh)");
     float inv[6];
@@ -192,6 +197,7 @@ static int project_host(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t 
                         const float trans[6], float oob, bool scale, float mult, float offset) {
     NL_REQUIRE(ctx && trans, "NULL argument");
     NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0, "negative image size");
+    NL_REQUIRE((long long)sw * sh <= 0x7fffffffll && (long long)dw * dh <= 0x7fffffffll, "image larger than int32 pixels (fits.go:40)");
     float inv[6];
     int rc = nl_transform_invert(trans, inv);
     if (rc != NL_OK) return rc;
