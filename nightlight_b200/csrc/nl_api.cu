@@ -103,6 +103,7 @@ int nl_ctx_destroy(nl_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->list) cudaFree(ctx->list);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int k = 0; k < 2; k++)
         if (ctx->frame[k]) cudaFree(ctx->frame[k]);
     cudaStreamDestroy(ctx->stream);

@@ -26,6 +26,9 @@ struct nl_ctx {
     size_t scratch_bytes = 0;
     void *frame[2] = {nullptr, nullptr};   // whole-frame staging of the host-pointer entry points (grown on demand, kept)
     size_t frame_bytes[2] = {0, 0};
+    void *pinned = nullptr;          // mapped pinned host memory: the star scan writes its count and candidates straight into it
+    void *pinned_dev = nullptr;      // (its device address)
+    size_t pinned_bytes = 0;
     void *list = nullptr;            // candidate list of the star scan (kept apart from `scratch`, which holds the row offsets)
     size_t list_bytes = 0;
     // nl_stack_apply keeps its two stripe lanes (context + job + result buffer each) between calls:

@@ -19,6 +19,7 @@
 
 #include <math.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 namespace nl {
@@ -124,60 +125,67 @@ int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, 
     return NL_OK;
 }
 
-// pass 1: per-row counts and offsets; *count = number of candidates in the frame
-static int bright_count(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius, int *count) {
+// Both passes queued back to back with ONE host round trip: the count and the candidates land in mapped pinned host
+// memory (the write pass stores them there directly, a few thousand 24-byte records), sized from the previous frames'
+// yield; a frame that overflows it repeats the write pass into a larger buffer.
+// *count = candidates in the frame; `stars` receives min(count, keep_max) of them in raster order.
+static int bright_scan(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius, int keep_max,
+                       std::vector<nl_star> *stars_vec, nl_star *stars_ptr, int *count) {
     *count = 0;
     if (len == 0) return NL_OK;
     const int rows = (len + width - 1) / width;
-    // scratch: row_count[rows], row_offset[rows], total
     const size_t ints = (size_t)2 * rows + 1;
     int rc = ensure_scratch(ctx, (ints * sizeof(int) + 255) & ~(size_t)255);
     if (rc != NL_OK) return rc;
     int *row_count = (int *)ctx->scratch, *row_offset = row_count + rows, *total = row_offset + rows;
     const int threads = 256, warps_per_cta = threads / 32;
     const unsigned grid = (unsigned)((rows + warps_per_cta - 1) / warps_per_cta);
+    auto ensure_pinned = [&](size_t entries) -> int {
+        const size_t need = 64 + sizeof(nl_star) * entries;
+        if (ctx->pinned_bytes >= need) return NL_OK;
+        if (ctx->pinned) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+        NL_CUDA(cudaHostAlloc(&ctx->pinned, need, cudaHostAllocMapped));
+        NL_CUDA(cudaHostGetDevicePointer(&ctx->pinned_dev, ctx->pinned, 0));
+        ctx->pinned_bytes = need;
+        return NL_OK;
+    };
+    rc = ensure_pinned(16384);
+    if (rc != NL_OK) return rc;
     bright_rows_kernel<false><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
                                                                 nullptr, nullptr, 0);
     NL_CUDA(cudaGetLastError());
     row_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(row_count, row_offset, rows, total);
     NL_CUDA(cudaGetLastError());
     ctx->launches += 2;
-    NL_CUDA(cudaMemcpyAsync(count, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    return NL_OK;
-}
-
-// pass 2 (after bright_count on the same frame): write the first `keep` candidates in raster order
-static int bright_write(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius,
-                        nl_star *host_out, int keep) {
-    if (keep <= 0 || len == 0) return NL_OK;
-    const int rows = (len + width - 1) / width;
-    int *row_count = (int *)ctx->scratch, *row_offset = row_count + rows;
-    const int threads = 256, warps_per_cta = threads / 32;
-    const unsigned grid = (unsigned)((rows + warps_per_cta - 1) / warps_per_cta);
-    // the list lives in its own (reused, grown on demand) allocation so the offsets in the context scratch stay valid
-    const size_t need = sizeof(nl_star) * (size_t)keep;
-    if (ctx->list_bytes < need) {
-        if (ctx->list) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFree(ctx->list)); ctx->list = nullptr; ctx->list_bytes = 0; }
-        const size_t grow = need + need / 2 + 4096;
-        NL_CUDA(cudaMalloc(&ctx->list, grow));
-        ctx->list_bytes = grow;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int slots = (int)std::min<size_t>((ctx->pinned_bytes - 64) / sizeof(nl_star), (size_t)0x7fffffff);
+        volatile int *host_total = (volatile int *)ctx->pinned;
+        nl_star *host_list = (nl_star *)((char *)ctx->pinned + 64);
+        nl_star *dev_list = (nl_star *)((char *)ctx->pinned_dev + 64);
+        bright_rows_kernel<true><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
+                                                                   row_offset, dev_list, slots);
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        NL_CUDA(cudaMemcpyAsync((void *)host_total, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int n = *host_total;
+        *count = n;
+        const int keep = n < keep_max ? n : keep_max;
+        if (keep > slots) {                                   // more candidates than the pinned list holds: grow, write again
+            rc = ensure_pinned((size_t)keep + (size_t)keep / 2);
+            if (rc != NL_OK) return rc;
+            continue;
+        }
+        if (stars_vec) { stars_vec->resize((size_t)(keep > 0 ? keep : 1)); stars_ptr = stars_vec->data(); }
+        if (keep > 0) memcpy(stars_ptr, host_list, sizeof(nl_star) * (size_t)keep);
+        return NL_OK;
     }
-    nl_star *dev_list = (nl_star *)ctx->list;
-    bright_rows_kernel<true><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
-                                                               row_offset, dev_list, keep);
-    NL_CUDA(cudaGetLastError());
-    ctx->launches++;
-    NL_CUDA(cudaMemcpyAsync(host_out, dev_list, need, cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    return NL_OK;
+    return set_error(NL_E_CUDA, "star scan: candidate list did not fit after growing");
 }
 
 static int find_bright_dev(nl_ctx *ctx, const float *dev_data, int len, int width, float threshold, int radius,
                            nl_star *host_out, int cap, int *count) {
-    int rc = bright_count(ctx, dev_data, len, width, threshold, radius, count);
-    if (rc != NL_OK) return rc;
-    return bright_write(ctx, dev_data, len, width, threshold, radius, host_out, *count < cap ? *count : cap);
+    return bright_scan(ctx, dev_data, len, width, threshold, radius, cap, nullptr, host_out, count);
 }
 
 // ---- sparse per-star steps on the host -------------------------------------------------------
@@ -448,10 +456,7 @@ int nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data
     CtxGuard g(ctx);
     std::vector<nl_star> stars(1);
     if (len > 0) {
-        int rc = bright_count(ctx, dev_data, len, width, threshold, radius, &n);
-        if (rc != NL_OK) return rc;
-        stars.resize((size_t)(n > 0 ? n : 1));
-        rc = bright_write(ctx, dev_data, len, width, threshold, radius, stars.data(), n);
+        int rc = bright_scan(ctx, dev_data, len, width, threshold, radius, 0x7fffffff, &stars, nullptr, &n);
         if (rc != NL_OK) return rc;
     }
     int m = n;

@@ -178,7 +178,7 @@ def main():
             cnt = C.c_int32()
             ms = timed_rot([lambda im=im: nl.binding.check(lib.nl_find_bright_dev(ctx.handle, C.c_void_p(im.data_ptr()), w * h, w, 3000.0, 16,
                                                                                   out.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))) for im in imgs])
-            report("find_bright (2 scans + offsets + D2H of candidates)", "radius 16, %d candidates; %s" % (cnt.value, rot),
+            report("find_bright (2 scans + offsets, one host round trip)", "radius 16, %d candidates; %s" % (cnt.value, rot),
                    4.0 * w * h, ms, {"mpx_per_s": w * h / ms / 1e3, "note": "whole call incl. host sync; the image is read twice (count, write)"})
         if not only or "prestats" in only:
             st = (C.c_float * 4)()
