@@ -53,6 +53,20 @@ int ensure_frame(nl_ctx *ctx, int slot, size_t bytes, float **out) {
     return NL_OK;
 }
 
+int ensure_pinned(nl_ctx *ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return NL_OK;
+    if (ctx->pinned) {
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+        NL_CUDA(cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+    }
+    NL_CUDA(cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocMapped));
+    NL_CUDA(cudaHostGetDevicePointer(&ctx->pinned_dev, ctx->pinned, 0));
+    ctx->pinned_bytes = bytes;
+    return NL_OK;
+}
+
 }  // namespace nl
 
 using namespace nl;

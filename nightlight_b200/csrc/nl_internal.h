@@ -46,6 +46,7 @@ int set_error(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int ensure_scratch(nl_ctx *ctx, size_t bytes);
 int ensure_frame(nl_ctx *ctx, int slot, size_t bytes, float **out);     // nl_api.cu
+int ensure_pinned(nl_ctx *ctx, size_t bytes);                           // nl_api.cu: ctx->pinned (mapped), at least `bytes`
 int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total);   // nl_stars.cu
 void median_filter_sparse_host(float *data, int32_t len, int32_t width, const int32_t *indices, int64_t n);     // nl_stars.cu
 int fits_decode_launch(nl_ctx *ctx, const void *dev_raw, int bitpix, long long n, float bscale, float bzero, float *dev_dst);

@@ -741,25 +741,30 @@ int nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_
     ctx->launches++;
     rc = exclusive_scan_launch(ctx, seg_count, seg_offset, (int)n_seg, total);
     if (rc != NL_OK) return rc;
-    int n_bad = 0;
-    NL_CUDA(cudaMemcpyAsync(&n_bad, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    *count = n_bad;
-    const long long keep = n_bad < cap ? n_bad : cap;
-    if (keep <= 0) return NL_OK;
-    const size_t need = sizeof(int32_t) * (size_t)keep;
-    if (ctx->list_bytes < need) {
-        if (ctx->list) { NL_CUDA(cudaFree(ctx->list)); ctx->list = nullptr; ctx->list_bytes = 0; }
-        const size_t grow = need + need / 2 + 4096;
-        NL_CUDA(cudaMalloc(&ctx->list, grow));
-        ctx->list_bytes = grow;
+    // the write pass follows at once, into mapped pinned host memory sized from earlier frames: one host round trip
+    rc = ensure_pinned(ctx, 64 + sizeof(int32_t) * 65536);
+    if (rc != NL_OK) return rc;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const long long slots = (long long)((ctx->pinned_bytes - 64) / sizeof(int32_t));
+        volatile int *host_total = (volatile int *)ctx->pinned;
+        outlier_scan_kernel<true><<<grid, 256, 0, ctx->stream>>>(dev_tmp, len, lo, hi, seg_count, seg_offset,
+                                                                (int32_t *)((char *)ctx->pinned_dev + 64), slots);
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        NL_CUDA(cudaMemcpyAsync((void *)host_total, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int n_bad = *host_total;
+        *count = n_bad;
+        const long long keep = n_bad < cap ? n_bad : cap;
+        if (keep > slots) {                                   // more than the pinned list holds: grow, write again
+            rc = ensure_pinned(ctx, 64 + sizeof(int32_t) * (size_t)(keep + keep / 2));
+            if (rc != NL_OK) return rc;
+            continue;
+        }
+        if (keep > 0) memcpy(host_bpm, (char *)ctx->pinned + 64, sizeof(int32_t) * (size_t)keep);
+        return NL_OK;
     }
-    outlier_scan_kernel<true><<<grid, 256, 0, ctx->stream>>>(dev_tmp, len, lo, hi, seg_count, seg_offset, (int32_t *)ctx->list, keep);
-    NL_CUDA(cudaGetLastError());
-    ctx->launches++;
-    NL_CUDA(cudaMemcpyAsync(host_bpm, ctx->list, need, cudaMemcpyDeviceToHost, ctx->stream));
-    NL_CUDA(cudaStreamSynchronize(ctx->stream));
-    return NL_OK;
+    return set_error(NL_E_CUDA, "bad-pixel map: list did not fit after growing");
 }
 
 int nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,

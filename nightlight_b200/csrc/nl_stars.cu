@@ -140,16 +140,7 @@ static int bright_scan(nl_ctx *ctx, const float *dev_data, int len, int width, f
     int *row_count = (int *)ctx->scratch, *row_offset = row_count + rows, *total = row_offset + rows;
     const int threads = 256, warps_per_cta = threads / 32;
     const unsigned grid = (unsigned)((rows + warps_per_cta - 1) / warps_per_cta);
-    auto ensure_pinned = [&](size_t entries) -> int {
-        const size_t need = 64 + sizeof(nl_star) * entries;
-        if (ctx->pinned_bytes >= need) return NL_OK;
-        if (ctx->pinned) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
-        NL_CUDA(cudaHostAlloc(&ctx->pinned, need, cudaHostAllocMapped));
-        NL_CUDA(cudaHostGetDevicePointer(&ctx->pinned_dev, ctx->pinned, 0));
-        ctx->pinned_bytes = need;
-        return NL_OK;
-    };
-    rc = ensure_pinned(16384);
+    rc = ensure_pinned(ctx, 64 + sizeof(nl_star) * 16384);
     if (rc != NL_OK) return rc;
     bright_rows_kernel<false><<<grid, threads, 0, ctx->stream>>>(dev_data, len, width, rows, threshold, radius, row_count,
                                                                 nullptr, nullptr, 0);
@@ -172,7 +163,7 @@ static int bright_scan(nl_ctx *ctx, const float *dev_data, int len, int width, f
         *count = n;
         const int keep = n < keep_max ? n : keep_max;
         if (keep > slots) {                                   // more candidates than the pinned list holds: grow, write again
-            rc = ensure_pinned((size_t)keep + (size_t)keep / 2);
+            rc = ensure_pinned(ctx, 64 + sizeof(nl_star) * ((size_t)keep + (size_t)keep / 2));
             if (rc != NL_OK) return rc;
             continue;
         }
