@@ -68,6 +68,12 @@ int  nl_ctx_device(nl_ctx *ctx, int *device);
 int  nl_ctx_mem_info(nl_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 int  nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches);
+/* Tuning knobs for A/B measurements and tests; the library reads NO environment variables.  Keys:
+ *   "defer_passes"  "a,b,.."  after how many clipping passes (cumulative) each launch of the sigma / winsorized-sigma /
+ *                   linear-fit kernels hands its unfinished columns to the next launch; "0" = one launch, "" = built-in
+ *   "tile_width"    "32" | "16" | "8" | "1" | "0" (automatic): pixels per warp tile of the column kernel
+ *   "stats_debug", "stats_force_replay"  "0" | "1": diagnostics of the frame statistics (nl_stats) */
+int  nl_ctx_set_tuning(nl_ctx *ctx, const char *key, const char *value);
 
 /* ---- stacking: replaces OpStack.Apply + Stack* (internal/ops/stack/stack.go:115-227, 274-918) --
  * A job holds the N frames (or one row stripe of them: `pixels` = stripe pixels) in device memory,
@@ -76,6 +82,7 @@ int  nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches);
 int  nl_stack_begin(nl_ctx *ctx, int32_t n_frames, int64_t pixels, nl_stack_job **job);
 int  nl_stack_put_frame(nl_stack_job *job, int32_t i, const float *host, int64_t count);   /* H2D, async on the stream */
 int  nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_stride);   /* device-resident producers */
+int  nl_stack_job_shape(nl_stack_job *job, int32_t *n_frames, int64_t *pixels);
 /* Runs one stacking pass.  mode/sigma/ref_frame_loc are OpStack's fields (stack.go:66-73); weights is
  * NULL (StWeightNone) or n_frames floats from nl_get_weights.  The result (pixels floats) and the two
  * clip counters (stack.go:140, widened to 64 bit) go to host memory; blocks until they are there.
@@ -92,11 +99,20 @@ int  nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float s
 int  nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels, int64_t row_pixels,
                     int32_t n_stripes, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                     float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
+/* OpStack.Apply (stack.go:115) over SEVERAL devices in one call: host frame pointers in, ONE host image out.  The
+ * image's rows are dealt to the n_ctx contexts (one per device) in contiguous blocks -- device g stacks rows
+ * [g*H/G, (g+1)*H/G), the analogue of the reference's fan-out over pixel ranges (stack.go:134-147) -- and every device
+ * pipelines its block in n_stripes row stripes like nl_stack_apply, on a host thread of its own.  No exchange between
+ * devices.  Register the frames with nl_host_register (or allocate them pinned) for full PCIe speed. */
+int  nl_stack_apply_multi(nl_ctx *const *ctxs, int32_t n_ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels,
+                          int64_t row_pixels, int32_t n_stripes, int32_t mode, const float *weights, float sigma_low,
+                          float sigma_high, float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high);
 /* nl_stack_apply keeps its two stripe lanes (device buffers of 2 x n_frames x stripe pixels) in the context
  * between calls; this frees them early (nl_ctx_destroy does it too). */
 int  nl_stack_apply_release(nl_ctx *ctx);
 /* Same, result left in device memory (dev_out: pixels floats), asynchronous on the context's stream;
- * the clip counters are readable after nl_ctx_sync via nl_stack_clip_counts. */
+ * the clip counters are readable after nl_ctx_sync via nl_stack_clip_counts.  dev_out == NULL: count-only run, the
+ * kernels skip their result stores (trial stacks of the sigma goal-seek). */
 int  nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                       float ref_frame_loc, float *dev_out);
 /* Same, and the result is ALSO stored to n_peers (<= 8) further device buffers of `pixels` floats each:
@@ -107,7 +123,38 @@ int  nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, flo
 int  nl_stack_run_dev_bcast(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                             float ref_frame_loc, float *dev_out, float *const *peer_outs, int32_t n_peers);
 int  nl_stack_clip_counts(nl_stack_job *job, int64_t *clip_low, int64_t *clip_high);
+/* one stacking pass that only counts what it clips; blocks until the two totals are there */
+int  nl_stack_clip_counts_only(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                               int64_t *clip_low, int64_t *clip_high);
 int  nl_stack_end(nl_stack_job *job);
+
+/* ---- sigma goal-seek: FindSigmasAndStack / binarySearchAndStack / newtonMethodAndStack
+ * (internal/ops/stack/stackfindsigma.go:27-170 -- DEAD code in the reference, inside a comment block: parity
+ * unpinned).  Finds the clipping sigmas that reach target clip percentages: bisection on [1,11] per side for the
+ * sigma / winsorized-sigma modes, Newton's method for the linear fit (which, like the reference, measures the high
+ * side against the LOW target, :114,:155), at most 21 trial stacks.  The search is a state machine so that the trial
+ * totals may come from anywhere (one job, the row stripes of several GPUs summed, a batch):
+ *     nl_sigma_seek_begin(&s, ...);
+ *     while (!s.done) { run a count-only stack at (s.trial_low, s.trial_high); nl_sigma_seek_step(&s, clipLow, clipHigh); }
+ *     stack at (s.result_low, s.result_high)
+ * Plain data, caller-allocated; only the fields named above are for the caller. */
+typedef struct {
+    int32_t mode;                       /* resolved mode (never NL_ST_AUTO) */
+    int32_t done, converged, trials;
+    float   trial_low, trial_high;      /* sigmas of the next trial stack */
+    float   result_low, result_high;    /* valid when done */
+    /* internal state */
+    int32_t step, phase;
+    float   perc_low, perc_high, total;
+    float   low_l, low_r, low_m, high_l, high_r, high_m;
+    float   sig_lo, sig_hi, d_l, d_h, new_lo;
+} nl_sigma_seek;
+int  nl_sigma_seek_begin(nl_sigma_seek *s, int32_t mode, int32_t n_frames, int64_t pixels, float clip_perc_low, float clip_perc_high);
+int  nl_sigma_seek_step(nl_sigma_seek *s, int64_t clip_low, int64_t clip_high);   /* 1: done, 0: another trial, < 0: error */
+/* FindSigmasAndStack over one resident job: count-only trials, then one stack at the sigmas found */
+int  nl_find_sigmas_and_stack(nl_stack_job *job, int32_t mode, const float *weights, float ref_frame_loc, float clip_perc_low,
+                              float clip_perc_high, float *host_out, int64_t *clip_low, int64_t *clip_high, float *sigma_low,
+                              float *sigma_high, int32_t *trials);
 /* autoSelectStackingMode (stack.go:45-55) */
 int  nl_auto_select_mode(int32_t n_frames);
 /* getWeights (stack.go:231-270) on the per-frame scalars it reads (Exposure, Stats.Noise(), HFR). */
@@ -145,7 +192,8 @@ int  nl_estimate_noise(nl_ctx *ctx, const float *host_data, int32_t len, int32_t
  * nl_bad_pixel_map: pre.BadPixelMap (internal/ops/pre/badpixels.go:32-51): tmp = data - median3x3(data),
  *   stats of tmp (the reference's medianDiffStats; stats[3] is the medianDiffStats.StdDev() that star
  *   detection takes, findstars.go:134-169), indices with tmp < -stddev*sigma_low or tmp > stddev*sigma_high
- *   in ascending order.  *count = number found; the first min(count, cap) are written to bpm. */
+ *   in ascending order.  *count = number found; the first min(count, cap) are written to bpm.
+ * Device pointers may have any float alignment, except dev_tmp of nl_bad_pixel_map_dev (16 bytes). */
 int  nl_median_filter3x3(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float *host_out);
 int  nl_median_filter3x3_dev(nl_ctx *ctx, const float *dev_data, int32_t width, int32_t height, float *dev_out);
 int  nl_stats(nl_ctx *ctx, const float *host_data, int64_t len, float stats[4]);

@@ -21,6 +21,16 @@ class NightlightError(RuntimeError):
         self.code = code
 
 
+class SigmaSeek(C.Structure):
+    """nl_sigma_seek (include/nightlight_cuda.h): the state of the sigma goal-seek"""
+    _fields_ = [("mode", C.c_int32), ("done", C.c_int32), ("converged", C.c_int32), ("trials", C.c_int32),
+                ("trial_low", C.c_float), ("trial_high", C.c_float), ("result_low", C.c_float), ("result_high", C.c_float),
+                ("step", C.c_int32), ("phase", C.c_int32), ("perc_low", C.c_float), ("perc_high", C.c_float), ("total", C.c_float),
+                ("low_l", C.c_float), ("low_r", C.c_float), ("low_m", C.c_float), ("high_l", C.c_float), ("high_r", C.c_float),
+                ("high_m", C.c_float), ("sig_lo", C.c_float), ("sig_hi", C.c_float), ("d_l", C.c_float), ("d_h", C.c_float),
+                ("new_lo", C.c_float)]
+
+
 class Star(C.Structure):
     """star.Star, internal/star/findstars.go:30-37"""
     _fields_ = [("index", C.c_int32), ("value", C.c_float), ("x", C.c_float), ("y", C.c_float),
@@ -46,6 +56,14 @@ DECLARED_SYMBOLS = {
     "nl_ctx_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "nl_ctx_mem_info": (C.c_int, [_vp, _i64p, _i64p]),
     "nl_ctx_launch_count": (C.c_int, [_vp, _i64p]),
+    "nl_ctx_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "nl_stack_job_shape": (C.c_int, [_vp, _i32p, _i64p]),
+    "nl_stack_apply_multi": (C.c_int, [C.POINTER(_vp), C.c_int32, C.POINTER(_vp), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
+                                       C.c_float, C.c_float, C.c_float, _vp, _i64p, _i64p]),
+    "nl_stack_clip_counts_only": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, _i64p, _i64p]),
+    "nl_sigma_seek_begin": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_float]),
+    "nl_sigma_seek_step": (C.c_int, [_vp, C.c_int64, C.c_int64]),
+    "nl_find_sigmas_and_stack": (C.c_int, [_vp, C.c_int32, _fp, C.c_float, C.c_float, C.c_float, _vp, _i64p, _i64p, _fp, _fp, _i32p]),
     "nl_stack_begin": (C.c_int, [_vp, C.c_int32, C.c_int64, C.POINTER(_vp)]),
     "nl_stack_put_frame": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
     "nl_stack_frames_dev": (C.c_int, [_vp, C.POINTER(_vp), _i64p]),
@@ -186,6 +204,10 @@ class Context:
         n = C.c_int64()
         check(load_library().nl_ctx_exact_replays(self._h, C.byref(n)))
         return n.value
+
+    def set_tuning(self, key, value):
+        """nl_ctx_set_tuning: "defer_passes", "tile_width", "stats_debug", "stats_force_replay" (A/B measurements, tests)"""
+        check(load_library().nl_ctx_set_tuning(self._h, str(key).encode(), str(value).encode()))
 
     def mem_info(self):
         """(free, total) bytes of device memory"""
@@ -337,3 +359,20 @@ class StackJob:
         cl, ch = C.c_int64(), C.c_int64()
         check(load_library().nl_stack_clip_counts(self._h, C.byref(cl), C.byref(ch)))
         return cl.value, ch.value
+
+    def clip_counts_only(self, mode, weights=None, sigma_low=2.75, sigma_high=2.75):
+        """one stacking pass that only counts what it clips (no image written) -> (clipLow, clipHigh)"""
+        w, wp = self._weights(weights, self.n_frames)
+        cl, ch = C.c_int64(), C.c_int64()
+        check(load_library().nl_stack_clip_counts_only(self._h, int(mode), wp, sigma_low, sigma_high, C.byref(cl), C.byref(ch)))
+        return cl.value, ch.value
+
+    def find_sigmas_and_stack(self, mode, clip_perc_low, clip_perc_high, weights=None, ref_frame_loc=0.0):
+        """nl_find_sigmas_and_stack -> (result, clipLow, clipHigh, sigmaLow, sigmaHigh, trials)"""
+        w, wp = self._weights(weights, self.n_frames)
+        out = np.empty(self.pixels, dtype=np.float32)
+        cl, ch, sl, sh, tr = C.c_int64(), C.c_int64(), C.c_float(), C.c_float(), C.c_int32()
+        check(load_library().nl_find_sigmas_and_stack(self._h, int(mode), wp, ref_frame_loc, clip_perc_low, clip_perc_high,
+                                                      out.ctypes.data_as(_vp), C.byref(cl), C.byref(ch), C.byref(sl), C.byref(sh),
+                                                      C.byref(tr)))
+        return out, cl.value, ch.value, sl.value, sh.value, tr.value

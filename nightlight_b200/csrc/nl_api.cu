@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace nl {
 
@@ -93,6 +94,12 @@ int nl_ctx_create(int device, nl_ctx **out) {
         return set_error(NL_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
                          e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     if (device < 0 || device >= count) return set_error(NL_E_INVALID, "device %d out of range [0,%d)", device, count);
+    // the caller's current device is left as it was (a host that uses CUDA itself must not end up on another GPU)
+    struct Restore {
+        int prev = -1;
+        Restore() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+        ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
     NL_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     NL_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -113,7 +120,7 @@ int nl_ctx_create(int device, nl_ctx **out) {
 int nl_ctx_destroy(nl_ctx *ctx) {
     if (!ctx) return NL_OK;
     nl_stack_apply_release(ctx);
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->list) cudaFree(ctx->list);
@@ -127,7 +134,7 @@ int nl_ctx_destroy(nl_ctx *ctx) {
 
 int nl_ctx_sync(nl_ctx *ctx) {
     NL_REQUIRE(ctx, "ctx is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     return NL_OK;
 }
@@ -146,12 +153,40 @@ int nl_ctx_device(nl_ctx *ctx, int *device) {
 
 int nl_ctx_mem_info(nl_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes) {
     NL_REQUIRE(ctx, "ctx is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     size_t f = 0, t = 0;
     NL_CUDA(cudaMemGetInfo(&f, &t));
     if (free_bytes) *free_bytes = (int64_t)f;
     if (total_bytes) *total_bytes = (int64_t)t;
     return NL_OK;
+}
+
+// Tuning knobs for A/B measurements and tests.  The library reads no environment variables: whatever changes its
+// behaviour is set explicitly, per context.
+int nl_ctx_set_tuning(nl_ctx *ctx, const char *key, const char *value) {
+    NL_REQUIRE(ctx && key, "NULL argument");
+    const std::string k = key, v = value ? value : "";
+    if (k == "defer_passes") {
+        if (v.empty()) { ctx->defer_override = false; return NL_OK; }          // back to the built-in schedule
+        ctx->defer_override = true;
+        ctx->defer_n = 0;
+        for (const char *q = v.c_str(); *q && ctx->defer_n < 8;) {
+            const int x = atoi(q);
+            if (x > (ctx->defer_n ? ctx->defer_at[ctx->defer_n - 1] : 0)) ctx->defer_at[ctx->defer_n++] = x;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        return NL_OK;
+    }
+    if (k == "tile_width") {
+        const int w = atoi(v.c_str());
+        NL_REQUIRE(w == 0 || w == 32 || w == 16 || w == 8 || w == 1, "tile_width must be 0 (automatic), 32, 16, 8 or 1");
+        ctx->tile_width = w;
+        return NL_OK;
+    }
+    if (k == "stats_debug") { ctx->stats_debug = atoi(v.c_str()) != 0; return NL_OK; }
+    if (k == "stats_force_replay") { ctx->stats_force_replay = atoi(v.c_str()) != 0; return NL_OK; }
+    return set_error(NL_E_INVALID, "unknown tuning key '%s'", key);
 }
 
 int nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches) {
@@ -162,7 +197,7 @@ int nl_ctx_launch_count(nl_ctx *ctx, int64_t *launches) {
 
 int nl_dev_alloc(nl_ctx *ctx, int64_t bytes, void **dev) {
     NL_REQUIRE(ctx && dev && bytes >= 0, "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     cudaError_t e = cudaMalloc(dev, (size_t)(bytes > 0 ? bytes : 1));
     if (e == cudaErrorMemoryAllocation) return set_error(NL_E_NOMEM, "cudaMalloc of %lld bytes failed", (long long)bytes);
     NL_CUDA(e);
@@ -171,7 +206,7 @@ int nl_dev_alloc(nl_ctx *ctx, int64_t bytes, void **dev) {
 
 int nl_dev_free(nl_ctx *ctx, void *dev) {
     NL_REQUIRE(ctx, "ctx is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     NL_CUDA(cudaFree(dev));
     return NL_OK;
@@ -182,7 +217,7 @@ int nl_dev_free(nl_ctx *ctx, void *dev) {
 int nl_ipc_get_handle(nl_ctx *ctx, void *dev, unsigned char handle[64]) {
     NL_REQUIRE(ctx && dev && handle, "NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     cudaIpcMemHandle_t h;
     NL_CUDA(cudaIpcGetMemHandle(&h, dev));
     memcpy(handle, &h, 64);
@@ -191,7 +226,7 @@ int nl_ipc_get_handle(nl_ctx *ctx, void *dev, unsigned char handle[64]) {
 
 int nl_ipc_open_handle(nl_ctx *ctx, const unsigned char handle[64], void **dev) {
     NL_REQUIRE(ctx && dev && handle, "NULL argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     NL_CUDA(cudaIpcOpenMemHandle(dev, h, cudaIpcMemLazyEnablePeerAccess));
@@ -200,7 +235,7 @@ int nl_ipc_open_handle(nl_ctx *ctx, const unsigned char handle[64], void **dev) 
 
 int nl_ipc_close_handle(nl_ctx *ctx, void *dev) {
     NL_REQUIRE(ctx, "ctx is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     NL_CUDA(cudaIpcCloseMemHandle(dev));
     return NL_OK;
@@ -234,21 +269,21 @@ int nl_host_free_pinned(void *host) {
 
 int nl_memcpy_h2d(nl_ctx *ctx, void *dev, const void *host, int64_t bytes) {
     NL_REQUIRE(ctx && bytes >= 0, "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     NL_CUDA(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
     return NL_OK;
 }
 
 int nl_memcpy_d2h(nl_ctx *ctx, void *host, const void *dev, int64_t bytes) {
     NL_REQUIRE(ctx && bytes >= 0, "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     NL_CUDA(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return NL_OK;
 }
 
 int nl_memcpy_d2d(nl_ctx *ctx, void *dev_dst, const void *dev_src, int64_t bytes) {
     NL_REQUIRE(ctx && bytes >= 0, "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     NL_CUDA(cudaMemcpyAsync(dev_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return NL_OK;
 }

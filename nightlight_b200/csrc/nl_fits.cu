@@ -128,7 +128,7 @@ extern "C" {
 
 int nl_fits_decode_dev(nl_ctx *ctx, const void *dev_raw, int32_t bitpix, int64_t count, float bscale, float bzero, float *dev_dst) {
     NL_REQUIRE(ctx && count >= 0 && (count == 0 || (dev_raw && dev_dst)), "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     return fits_decode_launch(ctx, dev_raw, bitpix, count, bscale, bzero, dev_dst);
 }
 
@@ -136,7 +136,7 @@ int nl_fits_decode(nl_ctx *ctx, const void *host_raw, int32_t bitpix, int64_t co
     NL_REQUIRE(ctx && count >= 0 && (count == 0 || (host_raw && host_dst)), "bad argument");
     NL_REQUIRE(bitpix == 8 || bitpix == 16 || bitpix == 32 || bitpix == 64 || bitpix == -32 || bitpix == -64, "Unknown BITPIX value");
     if (count == 0) return NL_OK;
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t bytes_per = (size_t)(bitpix < 0 ? -bitpix : bitpix) / 8;
     const size_t raw_bytes = ((size_t)count * bytes_per + 255) & ~(size_t)255;
     int rc = ensure_scratch(ctx, raw_bytes + sizeof(float) * (size_t)count);
@@ -153,7 +153,7 @@ int nl_fits_decode(nl_ctx *ctx, const void *host_raw, int32_t bitpix, int64_t co
 int nl_fits_encode_dev(nl_ctx *ctx, const float *dev_src, int64_t count, void *dev_raw) {
     NL_REQUIRE(ctx && count >= 0 && (count == 0 || (dev_src && dev_raw)), "bad argument");
     if (count == 0) return NL_OK;
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     if ((((uintptr_t)dev_src | (uintptr_t)dev_raw) & 15) == 0) {
         long long vgrid = (count / 4 + 255) / 256;
         if (vgrid > (long long)ctx->sm_count * 16) vgrid = (long long)ctx->sm_count * 16;
@@ -174,7 +174,7 @@ int nl_fits_encode_dev(nl_ctx *ctx, const float *dev_src, int64_t count, void *d
 int nl_fits_encode(nl_ctx *ctx, const float *host_src, int64_t count, void *host_raw) {
     NL_REQUIRE(ctx && count >= 0 && (count == 0 || (host_src && host_raw)), "bad argument");
     if (count == 0) return NL_OK;
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t bytes = sizeof(float) * (size_t)count, half = (bytes + 255) & ~(size_t)255;
     int rc = ensure_scratch(ctx, 2 * half);
     if (rc != NL_OK) return rc;

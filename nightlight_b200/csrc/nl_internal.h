@@ -38,6 +38,13 @@ struct nl_ctx {
     float *lane_out[2] = {nullptr, nullptr};
     int64_t lane_px[2] = {0, 0};
     int lane_frames[2] = {0, 0};
+    // tuning knobs for A/B measurements and tests (nl_ctx_set_tuning); the library reads no environment variables
+    bool defer_override = false;     // "defer_passes": the deferral schedule below replaces the built-in one
+    int defer_n = 0;
+    int defer_at[8] = {0};
+    int tile_width = 0;              // "tile_width": 32 / 16 / 8 / 1 forces the tile width of the column kernel, 0 = automatic
+    bool stats_debug = false;        // "stats_debug": the frame statistics print their interval proofs to stderr
+    bool stats_force_replay = false; // "stats_force_replay": always replay the float64 chains in order
 };
 
 namespace nl {
@@ -74,5 +81,10 @@ struct CtxGuard {   // make the context's device current for the calling thread
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
+
+// every entry point that touches the device: make the context's device current, fail when that is impossible
+#define NL_GUARD(c)                                          \
+    nl::CtxGuard g(c);                                       \
+    if (!g.ok) return nl::set_error(NL_E_CUDA, "cudaSetDevice(%d) failed", (c)->device)
 
 }  // namespace nl

@@ -188,7 +188,7 @@ int nl_estimate_noise_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames
     volatile float denom = 6.0f * (float)(width - 2);
     denom = denom * (float)(height - 2);
     const float factor = (float)sqrt(0.5 * M_PI) / denom;
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t rows_bytes = sizeof(float) * (size_t)n_frames * (size_t)(height > 0 ? height : 1);
     int rc = ensure_scratch(ctx, ((rows_bytes + 255) & ~(size_t)255) + sizeof(float) * (size_t)n_frames);
     if (rc != NL_OK) return rc;
@@ -219,7 +219,7 @@ int nl_estimate_noise_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames
 int nl_estimate_noise(nl_ctx *ctx, const float *host_data, int32_t len, int32_t width, float *noise) {
     NL_REQUIRE(ctx && noise && len >= 0 && width > 0, "bad argument");
     NL_REQUIRE(host_data || len == 0, "NULL data");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     float *dev = nullptr;
     int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)(len > 0 ? len : 1), &dev);
     if (rc != NL_OK) return rc;

@@ -555,7 +555,7 @@ static int stats_dev(nl_ctx *ctx, const float *dev, long long n, float out[4]) {
     NL_CUDA(cudaMemcpyAsync(&h, dout, sizeof(StatOut), cudaMemcpyDeviceToHost, ctx->stream));
     NL_CUDA(cudaStreamSynchronize(ctx->stream));
     const double dn = (double)n;
-    if (getenv("NL_STATS_DEBUG"))
+    if (ctx->stats_debug)
         fprintf(stderr, "nl_stats: n=%lld amd64=%d mean_decided=%d total0=%.17g bound0=%.3g (rel %.3g) std_decided=%d total1=%.17g bound1=%.3g (rel %.3g)\n",
                 n, (int)amd64, h.mean_decided, h.total[0], h.bound[0], h.bound[0] / fabs(h.total[0]), h.std_decided, h.total[1], h.bound[1],
                 h.bound[1] / fabs(h.total[1]));
@@ -601,14 +601,14 @@ static int stats_dev(nl_ctx *ctx, const float *dev, long long n, float out[4]) {
         const float flo = finish(lo), fhi = finish(hi);
         uint32_t ulo, uhi;
         memcpy(&ulo, &flo, 4); memcpy(&uhi, &fhi, 4);
-        if (getenv("NL_STATS_DEBUG"))
+        if (ctx->stats_debug)
             fprintf(stderr, "nl_stats: second-level proof pass %d: fine terms %llu %llu %llu %llu, grid 2^%d, bound %.3g -> %s\n", mode, counts[0],
                     counts[1], counts[2], counts[3], g[0], b, ulo == uhi ? "proven" : "not proven");
         if (ulo != uhi) return 0;
         *total = t;                               // (without the tail: the caller appends it like the replay path does)
         return 1;
     };
-    const bool force_replay = getenv("NL_STATS_FORCE_REPLAY") != nullptr;      // development override: time the in-order replay
+    const bool force_replay = ctx->stats_force_replay;      // nl_ctx_set_tuning "stats_force_replay": time the in-order replay
     if (force_replay) h.mean_decided = h.std_decided = 0;
     if (!h.mean_decided) {
         double t;
@@ -681,7 +681,7 @@ int nl_ctx_exact_replays(nl_ctx *ctx, int64_t *replays) {
 int nl_median_filter3x3_dev(nl_ctx *ctx, const float *dev_data, int32_t width, int32_t height, float *dev_out) {
     NL_REQUIRE(ctx && width >= 0 && height >= 0, "bad argument");
     NL_REQUIRE((dev_data && dev_out) || width == 0 || height == 0, "NULL image pointer");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     return median_launch(ctx, dev_data, width, height, dev_out, false);
 }
 
@@ -689,7 +689,7 @@ int nl_median_filter3x3(nl_ctx *ctx, const float *host_data, int32_t len, int32_
     NL_REQUIRE(ctx && len >= 0 && width > 0 && len % width == 0, "bad image geometry");
     if (len == 0) return NL_OK;
     NL_REQUIRE(host_data && host_out, "NULL image pointer");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t bytes = sizeof(float) * (size_t)len, off = (bytes + 255) & ~(size_t)255;
     int rc = ensure_scratch(ctx, 2 * off);
     if (rc != NL_OK) return rc;
@@ -704,13 +704,23 @@ int nl_median_filter3x3(nl_ctx *ctx, const float *host_data, int32_t len, int32_
 
 int nl_stats_dev(nl_ctx *ctx, const float *dev_data, int64_t len, float stats[4]) {
     NL_REQUIRE(ctx && dev_data && stats, "NULL argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
+    if ((uintptr_t)dev_data & 15) {
+        // the passes read float4 vectors: a frame that does not start on 16 bytes (e.g. frame k of a stack job whose
+        // pixel count is not a multiple of four) is staged into the context's aligned frame buffer first
+        NL_REQUIRE(len >= 1, "statistics of an empty array");
+        float *aligned = nullptr;
+        int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &aligned);
+        if (rc != NL_OK) return rc;
+        NL_CUDA(cudaMemcpyAsync(aligned, dev_data, sizeof(float) * (size_t)len, cudaMemcpyDeviceToDevice, ctx->stream));
+        dev_data = aligned;
+    }
     return stats_dev(ctx, dev_data, len, stats);
 }
 
 int nl_stats(nl_ctx *ctx, const float *host_data, int64_t len, float stats[4]) {
     NL_REQUIRE(ctx && host_data && stats && len >= 1, "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     float *dev = nullptr;
     int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &dev);
     if (rc != NL_OK) return rc;
@@ -724,7 +734,8 @@ int nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_
     NL_REQUIRE(ctx && count && stats && width > 0 && len >= 1 && len % width == 0, "bad argument");
     NL_REQUIRE(len <= INT32_MAX, "frame too large for int32 indices");
     NL_REQUIRE(dev_data && dev_tmp && (host_bpm || cap == 0) && cap >= 0, "NULL pointer");
-    CtxGuard g(ctx);
+    NL_REQUIRE(((uintptr_t)dev_tmp & 15) == 0, "dev_tmp must be 16-byte aligned (its statistics are read as float4 vectors)");
+    NL_GUARD(ctx);
     *count = 0;
     int rc = median_launch(ctx, dev_data, width, (int)(len / width), dev_tmp, true);
     if (rc != NL_OK) return rc;
@@ -770,7 +781,7 @@ int nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_
 int nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
                      int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]) {
     NL_REQUIRE(ctx && host_data && len >= 1, "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     float *dev = nullptr, *tmp = nullptr;
     const size_t bytes = sizeof(float) * (size_t)len;
     int rc = ensure_frame(ctx, 0, bytes, &dev);
@@ -793,7 +804,7 @@ static int op_bad_pixel(nl_ctx *ctx, float *dev_data, bool upload, float *host_d
     NL_REQUIRE(ctx && host_data && removed && stats && len >= 1 && width > 0, "bad argument");
     *removed = 0;
     if (sigma_low == 0.0f || sigma_high == 0.0f) return NL_OK;          // :181-183
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t bytes = sizeof(float) * (size_t)len;
     float *tmp = nullptr;
     int rc = ensure_frame(ctx, 1, bytes, &tmp);

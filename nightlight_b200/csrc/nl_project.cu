@@ -135,7 +135,7 @@ static int project_launch(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t
     if (rc != NL_OK) return rc;
     if (dw == 0 || dh == 0) return NL_OK;
     NL_REQUIRE(dev_dst && (dev_src || sw == 0 || sh == 0), "NULL image pointer");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
     dim3 block(PBX, PBY);
     dim3 grid((dw + block.x - 1) / block.x, (dh + PR * block.y - 1) / (PR * block.y));
@@ -179,7 +179,7 @@ int nl_project_scatter_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_
     sc.row0[n_stripes] = dh;
     if (dw == 0 || dh == 0) return NL_OK;
     NL_REQUIRE(dev_src || sw == 0 || sh == 0, "NULL image pointer");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     Affine a{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
     dim3 block(64, 4);
     dim3 grid((dw + block.x - 1) / block.x, (dh + 4 * block.y - 1) / (4 * block.y));
@@ -203,7 +203,7 @@ static int project_host(nl_ctx *ctx, const float *host_src, int32_t sw, int32_t 
     if (rc != NL_OK) return rc;
     if (dw == 0 || dh == 0) return NL_OK;
     NL_REQUIRE(host_dst && (host_src || sw == 0 || sh == 0), "NULL image pointer");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t sbytes = sizeof(float) * (size_t)sw * sh, dbytes = sizeof(float) * (size_t)dw * dh;
     const size_t soff = (sbytes + 255) & ~(size_t)255;
     rc = ensure_scratch(ctx, soff + dbytes + 256);

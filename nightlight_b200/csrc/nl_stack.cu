@@ -19,6 +19,8 @@
 // nl_stack_sigma.cu / nl_stack_winsor.cu / nl_stack_linfit.cu.
 #include "nl_stack_kernel.cuh"
 
+#include <thread>
+
 namespace nl {
 
 // ---- StackMean / StackMeanWeighted (stack.go:307-366) ----------------------------------------
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256, NL_MEAN_MINB) stack_mean_kernel(StackArgs
 #pragma unroll
         for (int c = 0; c < V; c++)
             r[c] = num[c] == 0 ? a.ref_loc : __fdiv_rn(sum[c], W ? wsum[c] : (float)num[c]);
+        if (!a.out) continue;
         if (V == 4) {
             const float4 q = make_float4(r[0], r[1 % V], r[2 % V], r[3 % V]);
             *reinterpret_cast<float4 *>(a.out + p) = q;
@@ -122,8 +125,11 @@ static bool make_frame_tensor_map(nl_stack_job *job) {
 template <bool W>
 static int launch_mean(nl_stack_job *job, const StackArgs &args) {
     nl_ctx *ctx = job->ctx;
-    const bool vec = (job->pixels % 4) == 0;
-    const long long groups = vec ? job->pixels / 4 : job->pixels;
+    // float4 path: frame rows (stride), the result and every peer copy 16-byte aligned; else one pixel per thread
+    uintptr_t align = (uintptr_t)args.frames | (uintptr_t)args.out | (uintptr_t)(args.stride * 4);
+    for (int e = 0; e < args.n_peers; e++) align |= (uintptr_t)args.peer_out[e];
+    const bool vec = (args.pixels % 4) == 0 && (align & 15) == 0;
+    const long long groups = vec ? args.pixels / 4 : args.pixels;
     long long grid = (groups + 255) / 256;
     const long long cap = (long long)ctx->sm_count * 8;
     if (grid > cap) grid = cap;
@@ -144,7 +150,7 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     if (mode == NL_ST_MAD_SIGMA && weighted)
         return set_error(NL_E_UNSUPPORTED, "MADSigma stacking with weights is still unimplemented");         // stack.go:185
     NL_CUDA(cudaMemsetAsync(job->clip, 0, NL_JOB_COUNTERS * sizeof(unsigned long long), ctx->stream));
-    if (job->pixels == 0) return NL_OK;
+    if (job->active == 0) return NL_OK;
     if (weighted)
         NL_CUDA(cudaMemcpyAsync(job->weights, host_weights, sizeof(float) * job->n, cudaMemcpyHostToDevice, ctx->stream));
     if (mode == NL_ST_LINEAR_FIT && !job->ramp_ready) {
@@ -156,7 +162,7 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     if (!job->tmap_ok && (job->pixels % 4) == 0 && job->pixels < (1ll << 31)) job->tmap_ok = make_frame_tensor_map(job);
     StackArgs a;
     a.use_tma = job->tmap_ok ? 1 : 0;
-    a.frames = job->frames; a.stride = job->pixels; a.pixels = job->pixels; a.n = job->n;
+    a.frames = job->frames; a.stride = job->pixels; a.pixels = job->active; a.n = job->n;
     a.weights = weighted ? job->weights : nullptr; a.ramp = job->ramp;
     a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip; a.tile_counter = job->clip + 2;
     a.defer_passes = 0; a.phase = 0; a.pool_in = StackArgs::Pool{nullptr, nullptr, nullptr, nullptr, job->clip + 3, 0};
@@ -213,9 +219,9 @@ int nl_stack_begin(nl_ctx *ctx, int32_t n_frames, int64_t pixels, nl_stack_job *
     *out = nullptr;
     NL_REQUIRE(n_frames >= 1, "n_frames must be >= 1");
     NL_REQUIRE(pixels >= 0, "pixels must be >= 0");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     nl_stack_job *j = new nl_stack_job();
-    j->ctx = ctx; j->n = n_frames; j->pixels = pixels;
+    j->ctx = ctx; j->n = n_frames; j->pixels = pixels; j->active = pixels;
     size_t frame_bytes = sizeof(float) * (size_t)n_frames * (size_t)(pixels > 0 ? pixels : 1);
     cudaError_t e = cudaMalloc(&j->frames, frame_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&j->out, sizeof(float) * (size_t)(pixels > 0 ? pixels : 1));
@@ -240,7 +246,7 @@ int nl_stack_put_frame(nl_stack_job *job, int32_t i, const float *host, int64_t 
     NL_REQUIRE(job && host, "NULL argument");
     NL_REQUIRE(i >= 0 && i < job->n, "frame index out of range");
     NL_REQUIRE(count == job->pixels, "frame size differs from the job's pixel count");
-    CtxGuard g(job->ctx);
+    NL_GUARD(job->ctx);
     NL_CUDA(cudaMemcpyAsync(job->frames + (size_t)i * job->pixels, host, sizeof(float) * (size_t)count,
                             cudaMemcpyHostToDevice, job->ctx->stream));
     return NL_OK;
@@ -257,7 +263,7 @@ int nl_stack_put_frame_raw(nl_stack_job *job, int32_t i, const void *host_raw, i
     NL_REQUIRE(bitpix == 8 || bitpix == 16 || bitpix == 32 || bitpix == 64 || bitpix == -32 || bitpix == -64, "Unknown BITPIX value");
     if (count == 0) return NL_OK;
     nl_ctx *ctx = job->ctx;
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const size_t bytes = (size_t)count * (size_t)(bitpix < 0 ? -bitpix : bitpix) / 8;
     // two staging halves used alternately: the upload of frame i+1 may start while frame i is decoded
     const size_t half = (bytes + 255) & ~(size_t)255;
@@ -266,6 +272,13 @@ int nl_stack_put_frame_raw(nl_stack_job *job, int32_t i, const void *host_raw, i
     void *stage = (char *)ctx->scratch + (size_t)(i & 1) * half;
     NL_CUDA(cudaMemcpyAsync(stage, host_raw, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return fits_decode_launch(ctx, stage, bitpix, count, bscale, bzero, job->frames + (size_t)i * job->pixels);
+}
+
+int nl_stack_job_shape(nl_stack_job *job, int32_t *n_frames, int64_t *pixels) {
+    NL_REQUIRE(job, "NULL argument");
+    if (n_frames) *n_frames = job->n;
+    if (pixels) *pixels = job->pixels;
+    return NL_OK;
 }
 
 int nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_stride) {
@@ -277,8 +290,8 @@ int nl_stack_frames_dev(nl_stack_job *job, float **dev_frames, int64_t *frame_st
 
 int nl_stack_run_dev(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                      float ref_frame_loc, float *dev_out) {
-    NL_REQUIRE(job && (dev_out || job->pixels == 0), "NULL argument");
-    CtxGuard g(job->ctx);
+    NL_REQUIRE(job, "NULL argument");              // dev_out == NULL: clip totals only, no image is written
+    NL_GUARD(job->ctx);
     int rc = stack_launch(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, dev_out);
     if (rc != NL_OK) return rc;
     NL_CUDA(cudaMemcpyAsync(job->clip_host, job->clip, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -290,12 +303,8 @@ int nl_stack_run_dev_bcast(nl_stack_job *job, int32_t mode, const float *weights
                            float ref_frame_loc, float *dev_out, float *const *peer_outs, int32_t n_peers) {
     NL_REQUIRE(job && (dev_out || job->pixels == 0), "NULL argument");
     NL_REQUIRE(n_peers >= 0 && n_peers <= NL_MAX_PEERS && (n_peers == 0 || peer_outs), "bad peer list");
-    const bool vec = (job->pixels % 4) == 0;
-    for (int e = 0; e < n_peers; e++) {
-        NL_REQUIRE(peer_outs[e], "NULL peer pointer");
-        NL_REQUIRE(!vec || (reinterpret_cast<uintptr_t>(peer_outs[e]) % 16) == 0, "peer stripes must be 16-byte aligned");
-    }
-    CtxGuard g(job->ctx);
+    for (int e = 0; e < n_peers; e++) NL_REQUIRE(peer_outs[e], "NULL peer pointer");
+    NL_GUARD(job->ctx);
     int rc = stack_launch(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, dev_out, peer_outs, n_peers);
     if (rc != NL_OK) return rc;
     NL_CUDA(cudaMemcpyAsync(job->clip_host, job->clip, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -310,10 +319,22 @@ int nl_stack_clip_counts(nl_stack_job *job, int64_t *clip_low, int64_t *clip_hig
     return NL_OK;
 }
 
+// One stacking pass that only counts what it clips (the trial stacks of the sigma goal-seek): the column kernel
+// runs as usual, the result stores are skipped.
+int nl_stack_clip_counts_only(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                              int64_t *clip_low, int64_t *clip_high) {
+    NL_REQUIRE(job, "NULL argument");
+    int rc = nl_stack_run_dev(job, mode, weights, sigma_low, sigma_high, 0.0f, nullptr);
+    if (rc != NL_OK) return rc;
+    rc = nl_ctx_sync(job->ctx);
+    if (rc != NL_OK) return rc;
+    return nl_stack_clip_counts(job, clip_low, clip_high);
+}
+
 int nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float sigma_low, float sigma_high,
                  float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
     NL_REQUIRE(job && (host_out || job->pixels == 0), "NULL argument");
-    CtxGuard g(job->ctx);
+    NL_GUARD(job->ctx);
     int rc = nl_stack_run_dev(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, job->out);
     if (rc != NL_OK) return rc;
     if (job->pixels > 0)
@@ -323,23 +344,29 @@ int nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float si
     return nl_stack_clip_counts(job, clip_low, clip_high);
 }
 
-// OpStack.Apply in one call for callers that can hand over all frames at once (C / C++ hosts; a Go host
-// pins the slices and passes a C array of their addresses): the image is cut into row stripes and two
-// internal contexts (streams) alternate, so the upload of stripe s+1 overlaps the stacking of stripe s and
-// the download of stripe s-1 -- the device never holds more than two stripes.
-int nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels, int64_t row_pixels,
-                   int32_t n_stripes, int32_t mode, const float *weights, float sigma_low, float sigma_high,
-                   float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
-    NL_REQUIRE(ctx && host_frames && n_frames >= 1 && pixels >= 0, "bad argument");
-    NL_REQUIRE(host_out || pixels == 0, "NULL output");
+}  // extern "C"
+
+namespace nl {
+
+// The pixel range [p_begin, p_end) of an image stacked from host frames through one context: the range is cut into
+// n_stripes row stripes that alternate on the context's two lanes (a lane = stream + job + result buffer), so the
+// upload of stripe s+1 overlaps the stacking of stripe s and the download of stripe s-1 -- the device never holds more
+// than two stripes.  The lanes are sized once for the largest stripe and kept in the context between calls; a ragged
+// last stripe runs in the same lane on fewer active pixels.
+static int stack_apply_range(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t p_begin, int64_t p_end,
+                             int64_t row_pixels, int32_t n_stripes, int32_t mode, const float *weights, float sigma_low,
+                             float sigma_high, float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
+    const int64_t pixels = p_end - p_begin;
     if (clip_low) *clip_low = 0;
     if (clip_high) *clip_high = 0;
-    if (mode < NL_ST_MEDIAN || mode > NL_ST_AUTO) return set_error(NL_E_INVALID, "invalid stacking mode");
-    if (pixels == 0) return NL_OK;
+    if (pixels <= 0) return NL_OK;
     if (row_pixels <= 0 || pixels % row_pixels != 0) row_pixels = pixels;       // no row structure known: one stripe
     const int64_t rows = pixels / row_pixels;
     if (n_stripes < 1) n_stripes = 8;
     if (n_stripes > rows) n_stripes = (int32_t)rows;
+    const int64_t stripe_rows = (rows + n_stripes - 1) / n_stripes;             // all stripes but the last
+    n_stripes = (int32_t)((rows + stripe_rows - 1) / stripe_rows);
+    const int64_t lane_px = stripe_rows * row_pixels;
     const int lanes = n_stripes > 1 ? 2 : 1;
     int64_t tot_lo = 0, tot_hi = 0;
     int rc = NL_OK;
@@ -351,26 +378,42 @@ int nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frame
         tot_lo += a; tot_hi += b;
         return r;
     };
-    for (int l = 0; l < lanes && rc == NL_OK; l++)
-        if (!ctx->lane_ctx[l]) rc = nl_ctx_create(ctx->device, &ctx->lane_ctx[l]);
-    for (int32_t si = 0; si < n_stripes && rc == NL_OK; si++) {
-        const int l = si % lanes;
-        const int64_t p0 = rows * si / n_stripes * row_pixels, p1 = rows * (si + 1) / n_stripes * row_pixels, px = p1 - p0;
-        if (si >= lanes) rc = collect(l);
-        if (rc == NL_OK && (px != ctx->lane_px[l] || n_frames != ctx->lane_frames[l] || !ctx->lane_job[l])) {   // (re)size the lane
+    for (int l = 0; l < lanes && rc == NL_OK; l++) {
+        if (!ctx->lane_ctx[l]) {
+            rc = nl_ctx_create(ctx->device, &ctx->lane_ctx[l]);
+            if (rc == NL_OK) {                               // the lanes inherit the tuning of their context
+                nl_ctx *lc = ctx->lane_ctx[l];
+                lc->defer_override = ctx->defer_override; lc->defer_n = ctx->defer_n;
+                for (int i = 0; i < 8; i++) lc->defer_at[i] = ctx->defer_at[i];
+                lc->tile_width = ctx->tile_width;
+            }
+        }
+        if (rc == NL_OK && (lane_px > ctx->lane_px[l] || n_frames != ctx->lane_frames[l] || !ctx->lane_job[l])) {   // (re)size the lane
             if (ctx->lane_job[l]) { nl_stack_end(ctx->lane_job[l]); ctx->lane_job[l] = nullptr; }
             if (ctx->lane_out[l]) { nl_dev_free(ctx->lane_ctx[l], ctx->lane_out[l]); ctx->lane_out[l] = nullptr; }
             ctx->lane_px[l] = 0;
-            rc = nl_stack_begin(ctx->lane_ctx[l], n_frames, px, &ctx->lane_job[l]);
-            if (rc == NL_OK) rc = nl_dev_alloc(ctx->lane_ctx[l], 4 * px, (void **)&ctx->lane_out[l]);
-            if (rc == NL_OK) { ctx->lane_px[l] = px; ctx->lane_frames[l] = n_frames; }
+            rc = nl_stack_begin(ctx->lane_ctx[l], n_frames, lane_px, &ctx->lane_job[l]);
+            if (rc == NL_OK) rc = nl_dev_alloc(ctx->lane_ctx[l], 4 * lane_px, (void **)&ctx->lane_out[l]);
+            if (rc == NL_OK) { ctx->lane_px[l] = lane_px; ctx->lane_frames[l] = n_frames; }
         }
+    }
+    for (int32_t si = 0; si < n_stripes && rc == NL_OK; si++) {
+        const int l = si % lanes;
+        nl_stack_job *job = ctx->lane_job[l];
+        const int64_t p0 = p_begin + si * lane_px;
+        const int64_t px = (si + 1 < n_stripes ? lane_px : p_end - p0);
+        if (si >= lanes) rc = collect(l);
+        if (rc != NL_OK) break;
+        NL_GUARD(job->ctx);
+        job->active = px;                                    // frames stay job->pixels apart; the run covers px of them
         for (int32_t k = 0; k < n_frames && rc == NL_OK; k++) {
-            if (!host_frames[k]) rc = set_error(NL_E_INVALID, "frame %d is NULL", k);
-            else rc = nl_stack_put_frame(ctx->lane_job[l], k, host_frames[k] + p0, px);
+            if (!host_frames[k]) { rc = set_error(NL_E_INVALID, "frame %d is NULL", k); break; }
+            cudaError_t e = cudaMemcpyAsync(job->frames + (size_t)k * job->pixels, host_frames[k] + p0, sizeof(float) * (size_t)px,
+                                            cudaMemcpyHostToDevice, job->ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "frame upload");
         }
         if (rc == NL_OK)
-            rc = nl_stack_run_dev(ctx->lane_job[l], mode, weights, sigma_low, sigma_high, ref_frame_loc, ctx->lane_out[l]);
+            rc = nl_stack_run_dev(job, mode, weights, sigma_low, sigma_high, ref_frame_loc, ctx->lane_out[l]);
         if (rc == NL_OK) rc = nl_memcpy_d2h(ctx->lane_ctx[l], host_out + p0, ctx->lane_out[l], 4 * px);
     }
     for (int l = 0; l < lanes && l < n_stripes && rc == NL_OK; l++) rc = collect(l);
@@ -382,6 +425,62 @@ int nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frame
     }
     if (clip_low) *clip_low = tot_lo;
     if (clip_high) *clip_high = tot_hi;
+    return NL_OK;
+}
+
+}  // namespace nl
+
+extern "C" {
+
+// OpStack.Apply in one call for callers that can hand over all frames at once (C / C++ hosts; a Go host
+// pins the slices and passes a C array of their addresses).
+int nl_stack_apply(nl_ctx *ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels, int64_t row_pixels,
+                   int32_t n_stripes, int32_t mode, const float *weights, float sigma_low, float sigma_high,
+                   float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
+    NL_REQUIRE(ctx && host_frames && n_frames >= 1 && pixels >= 0, "bad argument");
+    NL_REQUIRE(host_out || pixels == 0, "NULL output");
+    if (mode < NL_ST_MEDIAN || mode > NL_ST_AUTO) return set_error(NL_E_INVALID, "invalid stacking mode");
+    return stack_apply_range(ctx, host_frames, n_frames, 0, pixels, row_pixels, n_stripes, mode, weights, sigma_low, sigma_high,
+                             ref_frame_loc, host_out, clip_low, clip_high);
+}
+
+// OpStack.Apply over several devices in one call: the image's rows are dealt to the contexts in contiguous blocks
+// (device g stacks rows [g*H/G, (g+1)*H/G), SURVEY.md 8e -- the analogue of the reference's fan-out over pixel ranges,
+// stack.go:134-147), every device pipelines its block like nl_stack_apply on a host thread of its own, and all of them
+// write their rows of the one host image.  No exchange between devices: a pixel's column never leaves its GPU.
+int nl_stack_apply_multi(nl_ctx *const *ctxs, int32_t n_ctx, const float *const *host_frames, int32_t n_frames, int64_t pixels,
+                         int64_t row_pixels, int32_t n_stripes, int32_t mode, const float *weights, float sigma_low,
+                         float sigma_high, float ref_frame_loc, float *host_out, int64_t *clip_low, int64_t *clip_high) {
+    NL_REQUIRE(ctxs && n_ctx >= 1 && n_ctx <= 64 && host_frames && n_frames >= 1 && pixels >= 0, "bad argument");
+    NL_REQUIRE(host_out || pixels == 0, "NULL output");
+    for (int g = 0; g < n_ctx; g++) NL_REQUIRE(ctxs[g], "NULL context");
+    if (mode < NL_ST_MEDIAN || mode > NL_ST_AUTO) return set_error(NL_E_INVALID, "invalid stacking mode");
+    if (clip_low) *clip_low = 0;
+    if (clip_high) *clip_high = 0;
+    if (pixels == 0) return NL_OK;
+    if (row_pixels <= 0 || pixels % row_pixels != 0) row_pixels = pixels;
+    const int64_t rows = pixels / row_pixels;
+    std::vector<int> rc(n_ctx, NL_OK);
+    std::vector<std::string> err(n_ctx);
+    std::vector<int64_t> lo(n_ctx, 0), hi(n_ctx, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_ctx; g++) {
+        const int64_t r0 = rows * g / n_ctx, r1 = rows * (g + 1) / n_ctx;
+        if (r1 == r0) continue;
+        th.emplace_back([&, g, r0, r1]() {
+            rc[g] = stack_apply_range(ctxs[g], host_frames, n_frames, r0 * row_pixels, r1 * row_pixels, row_pixels, n_stripes, mode,
+                                      weights, sigma_low, sigma_high, ref_frame_loc, host_out, &lo[g], &hi[g]);
+            if (rc[g] != NL_OK) err[g] = nl_last_error();                    // (thread-local: carry it to the caller's thread)
+        });
+    }
+    for (auto &t : th) t.join();
+    int64_t tl = 0, thi = 0;
+    for (int g = 0; g < n_ctx; g++) {
+        if (rc[g] != NL_OK) return set_error(rc[g], "device %d: %s", ctxs[g]->device, err[g].c_str());
+        tl += lo[g]; thi += hi[g];
+    }
+    if (clip_low) *clip_low = tl;
+    if (clip_high) *clip_high = thi;
     return NL_OK;
 }
 
@@ -399,7 +498,7 @@ int nl_stack_apply_release(nl_ctx *ctx) {
 
 int nl_stack_end(nl_stack_job *job) {
     if (!job) return NL_OK;
-    CtxGuard g(job->ctx);
+    NL_GUARD(job->ctx);
     cudaStreamSynchronize(job->ctx->stream);
     if (job->frames) cudaFree(job->frames);
     if (job->out) cudaFree(job->out);
@@ -464,7 +563,7 @@ int nl_stack_incremental_dev(nl_ctx *ctx, float *dev_acc, const float *dev_light
     NL_REQUIRE(ctx && pixels >= 0, "bad argument");
     if (pixels == 0) return NL_OK;
     NL_REQUIRE(dev_acc && dev_light, "NULL argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     const bool vec = (((uintptr_t)dev_acc | (uintptr_t)dev_light) & 15) == 0;
     long long grid = ((vec ? pixels / 8 : pixels) + 255) / 256;
     if (grid > (long long)ctx->sm_count * 8) grid = (long long)ctx->sm_count * 8;
@@ -480,7 +579,7 @@ int nl_stack_incremental_finalize_dev(nl_ctx *ctx, float *dev_acc, int64_t pixel
     NL_REQUIRE(ctx && pixels >= 0, "bad argument");
     if (pixels == 0) return NL_OK;
     NL_REQUIRE(dev_acc, "NULL argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     float factor = 1.0f / weight_sum;    // stack.go:941
     const bool vec = ((uintptr_t)dev_acc & 15) == 0;
     long long grid = ((vec ? pixels / 4 : pixels) + 255) / 256;

@@ -78,6 +78,7 @@ __device__ __forceinline__ void tma_box_g2s(unsigned dst, const CUtensorMap *tma
 // the local copy, every warp stores its 128-byte result segment straight into the gathered image of
 // each peer GPU (peer-mapped memory over NVLink), so no separate all-gather pass runs afterwards.
 __device__ __forceinline__ void store_result(const StackArgs &a, long long p, float v) {
+    if (!a.out) return;                                  // count-only run (sigma goal-seek trials): clip totals, no image
     a.out[p] = v;
     for (int e = 0; e < a.n_peers; e++) a.peer_out[e][p] = v;
 }
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
                 if (MODE == ST_MEDIAN) negzero |= __float_as_uint(v) == 0x80000000u;
                 cur += (v == v) ? 1 : 0;
             }
+            if (!valid) cur = 0;      // a job run on fewer pixels than it was sized for: the columns beyond are not NaN-filled
         } else if (valid) {
             // unaligned frame rows or narrow tiles: gather the non-NaN samples through registers, 32 loads
             // in flight per lane, each a 128-byte row segment per warp
@@ -290,7 +292,8 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
 struct nl_stack_job {
     nl_ctx *ctx = nullptr;
     int n = 0;
-    long long pixels = 0;
+    long long pixels = 0;             // capacity = element stride between frames
+    long long active = 0;             // pixels a run covers (<= pixels; nl_stack_apply runs ragged last stripes in a lane sized once)
     float *frames = nullptr;          // [n][pixels]
     float *out = nullptr;             // [pixels], used by nl_stack_run
     float *weights = nullptr;         // [n]
@@ -335,7 +338,7 @@ inline int launch_column(nl_stack_job *job, const StackArgs &args) {
     int ctas_per_sm = 0;
     NL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const long long tiles = (job->pixels + S - 1) / S;
+    const long long tiles = (args.pixels + S - 1) / S;
     long long grid = (long long)ctx->sm_count * ctas_per_sm;
     const long long need = (tiles + warps - 1) / warps;
     if (grid > need && args.phase == 0) grid = need;       // (the pool's tile count is only known on the device)
@@ -352,21 +355,16 @@ inline int launch_column(nl_stack_job *job, const StackArgs &args) {
 //     7.5 -> 6.9 ms with {3};  winsorized clipping settles one pass earlier: 11.8 -> 10.7 ms with {2};
 //   the linear fit needs 4 .. 40 rejection rounds per pixel (mean 12, slowest of 32 pixels: 26.6), so its columns
 //     are regrouped several times.
-// NL_DEFER_PASSES (development override, A/B measurements): a comma list, "0" switches the deferral off.
+// nl_ctx_set_tuning(ctx, "defer_passes", "a,b,..") replaces the schedule (A/B measurements, tests); "0" switches the deferral off.
 struct DeferSchedule { int n; int at[8]; double frac[2]; };
-inline DeferSchedule defer_schedule(int mode) {
+inline DeferSchedule defer_schedule(int mode, const nl_ctx *ctx) {
     DeferSchedule d{0, {0}, {0.25, 0.0}};
     if (mode == ST_SIGMA) { d.n = 1; d.at[0] = 3; }
     else if (mode == ST_WINSOR) { d.n = 1; d.at[0] = 2; }
     else if (mode == ST_LINFIT) { d.n = 6; const int at[6] = {8, 12, 16, 20, 24, 30}; for (int i = 0; i < 6; i++) d.at[i] = at[i]; d.frac[0] = 0.75; d.frac[1] = 0.5; }
-    if (const char *e = getenv("NL_DEFER_PASSES")) {
-        d.n = 0;
-        for (const char *q = e; *q && d.n < 8;) {
-            const int v = atoi(q);
-            if (v > (d.n ? d.at[d.n - 1] : 0)) d.at[d.n++] = v;
-            while (*q && *q != ',') q++;
-            if (*q == ',') q++;
-        }
+    if (ctx->defer_override) {
+        d.n = ctx->defer_n;
+        for (int i = 0; i < d.n; i++) d.at[i] = ctx->defer_at[i];
         if (d.n > 1) { d.frac[0] = 1.0; d.frac[1] = 1.0; } else if (d.n == 1) { d.frac[0] = d.at[0] < 3 ? 1.0 : 0.25; }
     }
     return d;
@@ -422,10 +420,10 @@ inline bool ensure_pools(nl_stack_job *job, int idx_bytes, const double frac[2],
 template <int MODE, bool W, int S, typename IDX>
 inline int launch_deferred(nl_stack_job *job, const StackArgs &args) {
     if (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT) {
-        DeferSchedule d = defer_schedule(MODE);
+        DeferSchedule d = defer_schedule(MODE, job->ctx);
         // several regrouping launches only pay with many tiles per warp (each launch ends in a tail of half-idle SMs):
         // measured, 1024 frames x 65 536 pixels: 15.5 ms in one launch, 16.6 ms with six regroupings; x 1 M pixels: 223 -> 213 ms
-        if (d.n > 1 && !getenv("NL_DEFER_PASSES") && (job->pixels + S - 1) / S < 32ll * job->ctx->sm_count * 8) d.n = 0;
+        if (d.n > 1 && !job->ctx->defer_override && (job->pixels + S - 1) / S < 32ll * job->ctx->sm_count * 8) d.n = 0;
         StackArgs::Pool pools[2];
         if (d.n > 0 && ensure_pools(job, W ? (int)sizeof(IDX) : 0, d.frac, pools)) {
             StackArgs a2 = args;
@@ -468,8 +466,8 @@ inline int launch_column_i(nl_stack_job *job, const StackArgs &args) {
         const double score = (double)(warps > 8 ? 8 : warps) * wdt;
         if (score > best_score) { best_score = score; best = wdt; }
     }
-    if (const char *force = getenv("NL_TILE_WIDTH")) {             // development override (A/B measurements)
-        const int wdt = atoi(force);
+    if (job->ctx->tile_width) {                                    // nl_ctx_set_tuning "tile_width" (A/B measurements)
+        const int wdt = job->ctx->tile_width;
         if ((wdt == 32 || wdt == 16 || wdt == 8 || wdt == 1) && (per_pixel + 2 * gap) * wdt <= cap) best = wdt;
     }
     switch (best) {

@@ -411,7 +411,7 @@ int nl_find_bright_dev(nl_ctx *ctx, const float *dev_data, int32_t len, int32_t 
     NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
     NL_REQUIRE(out || cap == 0, "out is NULL");
     NL_REQUIRE(dev_data || len == 0, "data is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     return find_bright_dev(ctx, dev_data, len, width, threshold, radius, out, cap, count);
 }
 
@@ -423,7 +423,7 @@ int nl_find_bright(nl_ctx *ctx, const float *host_data, int32_t len, int32_t wid
     NL_REQUIRE(host_data || len == 0, "data is NULL");
     *count = 0;
     if (len == 0) return NL_OK;
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     float *dev = nullptr;
     int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &dev);
     if (rc != NL_OK) return rc;
@@ -444,7 +444,7 @@ int nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data
     int32_t n = 0;
     *count = 0; *sum_of_shifts = 0.0f; *avg_hfr = 0.0f;
     NL_REQUIRE((host_data && dev_data) || len == 0, "data is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     std::vector<nl_star> stars(1);
     if (len > 0) {
         int rc = bright_scan(ctx, dev_data, len, width, threshold, radius, 0x7fffffff, &stars, nullptr, &n);
@@ -467,7 +467,7 @@ int nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t widt
                   float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
                   nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr) {
     NL_REQUIRE(ctx && len >= 0 && (host_data || len == 0), "bad argument");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     float *dev = nullptr;
     if (len > 0) {
         int rc = ensure_frame(ctx, 0, sizeof(float) * (size_t)len, &dev);

@@ -35,7 +35,7 @@ extern "C" int nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64
     NL_REQUIRE(ctx && count >= 0, "bad argument");
     if (count == 0) return NL_OK;
     NL_REQUIRE(dev_dst, "dst is NULL");
-    CtxGuard g(ctx);
+    NL_GUARD(ctx);
     long long grid = (count + 255) / 256;
     if (grid > (long long)ctx->sm_count * 16) grid = (long long)ctx->sm_count * 16;
     synth_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_dst, p0, count, frame, seed);

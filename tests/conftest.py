@@ -63,3 +63,17 @@ def ctx():
     c = nl.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture
+def tuning(ctx):
+    """nl_ctx_set_tuning for one test; the session context goes back to the built-in settings afterwards"""
+    used = []
+
+    def set_(key, value):
+        used.append(key)
+        ctx.set_tuning(key, value)
+
+    yield set_
+    for key in used:
+        ctx.set_tuning(key, "" if key == "defer_passes" else "0")

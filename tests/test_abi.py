@@ -121,3 +121,54 @@ def test_partition_matches_oracle():
         for i in range(gnb):
             chunk = order[i * gbs:(i + 1) * gbs]
             assert chunk == sorted(chunk)
+
+
+def _seek_native(count_fn, mode, n, p, lo, hi):
+    """drive nl_sigma_seek_* (host code of the C ABI, no device work) with a clip-count function"""
+    lib = nl.load_library()
+    s = binding.SigmaSeek()
+    binding.check(lib.nl_sigma_seek_begin(C.byref(s), mode, n, p, lo, hi))
+    traj = []
+    while not s.done:
+        traj.append((s.trial_low, s.trial_high))
+        cl, ch = count_fn(s.trial_low, s.trial_high)
+        assert lib.nl_sigma_seek_step(C.byref(s), cl, ch) >= 0
+    return s.result_low, s.result_high, s.trials, s.converged, traj
+
+
+@pytest.mark.parametrize("mode", [2, 3, 5, 6, 0])
+def test_sigma_goal_seek_state_machine_matches_the_python_restatement(mode):
+    """a21: nl_sigma_seek_begin/step (C ABI) follow, trial by trial, the float32 restatement of the reference's
+    commented-out FindSigmasAndStack (ops.find_sigmas_and_stack) on synthetic clip-count curves -- smooth ones
+    that converge, flat ones that stop Newton's method, and ones that never reach the target (20-step limit)"""
+    n, p = 40, 100000
+    rng = np.random.default_rng(mode)
+    for case in range(40):
+        a, b = float(rng.uniform(0.5, 3.0)), float(rng.uniform(0.5, 3.0))
+        kind = case % 4
+        lo_t, hi_t = float(rng.uniform(0.05, 3.0)), float(rng.uniform(0.05, 3.0))
+
+        def counts(sl, sh):
+            if kind == 3:                                   # flat: derivative 0
+                return 1234, 4321
+            fl = np.exp(-a * sl) * 0.2 + (0.0 if kind != 2 else 0.05)
+            fh = np.exp(-b * sh) * 0.2 + (0.001 * sl if kind == 1 else 0.0)   # kind 1: the sides interact (linear fit)
+            return int(fl * n * p), int(fh * n * p)
+
+        trace = []
+
+        def stack_fn(sl, sh):
+            trace.append((np.float32(sl), np.float32(sh)))
+            cl, ch = counts(sl, sh)
+            return None, cl, ch
+
+        want = nl.find_sigmas_and_stack(stack_fn, mode, n, p, lo_t, hi_t)
+        got = _seek_native(counts, mode, n, p, lo_t, hi_t)
+        assert (np.float32(got[0]), np.float32(got[1])) == (np.float32(want[3]), np.float32(want[4])), (case, got, want)
+        # the python version's last call is the stack it returns; the native search counts trials only
+        resolved = nl.load_library().nl_auto_select_mode(n) if mode == 6 else mode
+        if resolved in (2, 3, 5):
+            assert [tuple(np.float32(x) for x in t) for t in got[4]] == trace, case
+            assert got[2] == len(trace)
+        else:
+            assert got[4] == [] and got[:2] == (0.0, 0.0)

@@ -204,3 +204,33 @@ def test_resident_frame_pipeline_one_upload(ctx):
         assert np.float32(hfr.value).view(np.uint32) == want[2].view(np.uint32)
     finally:
         ctx.dev_free(dev)
+
+
+def test_stats_dev_of_a_frame_that_is_not_16_byte_aligned(ctx, numerics):
+    """nl_stats_dev on frame k of a stack job whose pixel count is not a multiple of four (the frame then starts on
+    an odd float): the float4 passes must not fault; nl_bad_pixel_map_dev rejects an unaligned scratch image"""
+    import ctypes as C
+    lib = nl.load_library()
+    w, h = 17, 9                                       # 153 pixels per frame
+    imgs = [frame(w, h, 500 + k).ravel() for k in range(3)]
+    with nl.StackJob(ctx, 3, w * h) as job:
+        for k in range(3):
+            job.put_frame(k, imgs[k])
+        base, stride = job.frames_dev
+        for k in range(3):
+            st = np.zeros(4, np.float32)
+            nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(base + 4 * k * stride), w * h, st.ctypes.data_as(C.POINTER(C.c_float))))
+            want = O.stats(imgs[k], amd64=numerics)
+            assert np.array_equal(st.view(np.uint32), want.view(np.uint32)), k
+        tmp = ctx.dev_alloc(4 * (w * h + 8))
+        try:
+            cnt, st = C.c_int64(), np.zeros(4, np.float32)
+            rc = lib.nl_bad_pixel_map_dev(ctx.handle, C.c_void_p(base + 4 * stride), w * h, w, 3.0, 5.0, C.c_void_p(tmp + 4), None, 0,
+                                          C.byref(cnt), st.ctypes.data_as(C.POINTER(C.c_float)))
+            assert rc == nl.binding.NL_E_INVALID and b"16-byte aligned" in lib.nl_last_error()
+            nl.binding.check(lib.nl_bad_pixel_map_dev(ctx.handle, C.c_void_p(base + 4 * stride), w * h, w, 3.0, 5.0, C.c_void_p(tmp), None, 0,
+                                                      C.byref(cnt), st.ctypes.data_as(C.POINTER(C.c_float))))
+            bpm, want, _ = O.bad_pixel_map(imgs[1], w, 3.0, 5.0, amd64=numerics)
+            assert cnt.value == bpm.size and np.array_equal(st.view(np.uint32), want.view(np.uint32))
+        finally:
+            ctx.dev_free(tmp)

@@ -10,7 +10,7 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import nightlight_b200 as nl  # noqa: E402
 from oracle import oracle as O  # noqa: E402
-from util import GOLDEN, MODE_ID, bits_equal, first_mismatch, from_hex, hx, kats, mode_cases, weights_for  # noqa: E402
+from util import GOLDEN, MODE_ID, bits_equal, first_mismatch, from_hex, hx, kats, mode_cases, synth_frames_threaded, weights_for  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -181,11 +181,30 @@ def test_stripes_equal_whole(ctx):
     assert bits_equal(np.concatenate(parts), whole[0]) and (cl, ch) == whole[1:]
 
 
+@pytest.mark.parametrize("mode,weighted", [("sigma", False), ("winsor", True)])
+def test_full_image_every_pixel_c2(ctx, mode, weighted):
+    """BASELINE configs[1] at size: 256 x 4096x4096 fp32 (16 GiB resident), the metric's sigma-clip mode and the
+    config's own winsorized + weighted mode.  The frames are generated twice -- on the device (nl_synth_fill_dev)
+    and on the host (the oracle's generator) -- and EVERY one of the 16.7 M stacked pixels and the exact clip totals
+    must equal the CPU restatement of the reference (all host threads, the reference's 8 MiB work packages)."""
+    n, pixels = 256, 4096 * 4096
+    w = weights_for(n) if weighted else None
+    with nl.StackJob(ctx, n, pixels) as job:
+        job.synth_fill(0)
+        res, cl, ch = job.run(MODE_ID[mode], w)
+    frames = synth_frames_threaded(n, 0, pixels)
+    want, wl, wh = O.stack(frames, mode, weights=w, threads=os.cpu_count() or 1)
+    del frames
+    assert bits_equal(res, want), first_mismatch(res, want)
+    assert (cl, ch) == (wl, wh)
+    assert not np.isnan(res).any()
+
+
 @pytest.mark.parametrize("mode,weighted,n,pixels", [
-    ("sigma", False, 256, 4096 * 4096),        # BASELINE config 2 headline: 256 x 4096^2, 16 GiB resident
-    ("winsor", True, 256, 4096 * 512),         # config 2's winsorized + weighted variant on a 512-row stripe
     ("linfit", False, 64, 6000 * 500),
     ("median", False, 256, 4096 * 512),
+    ("linfit", False, 1024, 8192 * 64),        # configs[3] depth and row width: 1024 frames, 8192-pixel rows (8-pixel tiles)
+    ("sigma", False, 1024, 8192 * 64),
 ])
 def test_full_size_sampled_tiles(ctx, mode, weighted, n, pixels):
     """Frames generated on the device at full size; the oracle regenerates sampled tiles from the same
@@ -195,11 +214,12 @@ def test_full_size_sampled_tiles(ctx, mode, weighted, n, pixels):
         job.synth_fill(0)
         res, cl, ch = job.run(MODE_ID[mode], w)
     rng = np.random.default_rng(2024)
-    starts = [0, pixels - 4096] + [int(s) for s in rng.integers(0, pixels - 4096, 6)]
+    span = 4096 if n <= 256 else 512
+    starts = [0, pixels - span] + [int(s) for s in rng.integers(0, pixels - span, 6)]
     for s in starts:
-        frames = O.synth_frames(n, s, 4096)
+        frames = O.synth_frames(n, s, span)
         want, _, _ = O.stack(frames, mode, weights=w)
-        assert bits_equal(res[s:s + 4096], want), (s, first_mismatch(res[s:s + 4096], want))
+        assert bits_equal(res[s:s + span], want), (s, first_mismatch(res[s:s + span], want))
     assert not np.isnan(res).any()
     if mode != "median":
         frac = (cl + ch) / (n * pixels)
@@ -313,11 +333,11 @@ def test_random_shapes_and_modes_fuzz(ctx, seed):
 
 @pytest.mark.parametrize("defer", ["1", "2", "3", "0", "1,2,4", "2,3,5,8,13"])
 @pytest.mark.parametrize("mode,weighted", [("sigma", False), ("sigma", True), ("winsor", False), ("winsor", True), ("linfit", False)])
-def test_deferred_clipping_passes_pool_and_overflow(ctx, monkeypatch, mode, weighted, defer):
+def test_deferred_clipping_passes_pool_and_overflow(ctx, tuning, mode, weighted, defer):
     """Late clipping passes are deferred to a pool of unfinished columns and finished by a second launch; the pool
     holds a quarter of the pixels, the overflow finishes in place.  Heavy-tailed samples make most pixels need
     many passes, so with an early limit the pool overflows; every variant must equal the oracle bit for bit."""
-    monkeypatch.setenv("NL_DEFER_PASSES", defer)
+    tuning("defer_passes", defer)
     rng = np.random.default_rng(len(defer) * 7 + len(mode) + weighted)
     n, p = 96, 32 * 61 + 5                              # 32-pixel tiles and a ragged last tile
     frames = (rng.standard_t(2.0, size=(n, p)) * 25 + 500).astype(np.float32)
@@ -330,9 +350,9 @@ def test_deferred_clipping_passes_pool_and_overflow(ctx, monkeypatch, mode, weig
 
 @pytest.mark.parametrize("defer", ["1", "3", "2,4,7"])
 @pytest.mark.parametrize("n", [520, 1030])
-def test_deferred_passes_on_narrow_tiles(ctx, monkeypatch, n, defer):
+def test_deferred_passes_on_narrow_tiles(ctx, tuning, n, defer):
     """more than 256 frames: 16- and 8-pixel tiles; the pools then hold tiles of that width"""
-    monkeypatch.setenv("NL_DEFER_PASSES", defer)
+    tuning("defer_passes", defer)
     rng = np.random.default_rng(n + len(defer))
     p = 16 * 7 + 5
     frames = (rng.standard_t(2.0, size=(n, p)) * 25 + 500).astype(np.float32)
@@ -375,3 +395,124 @@ def test_incremental_kernels_vector_and_scalar_paths(ctx, pixels, offset):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     finally:
         ctx.dev_free(dev)
+
+
+def test_stack_apply_multi_contexts_one_image(ctx):
+    """nl_stack_apply_multi: all host frame pointers in, ONE host image out, the rows dealt to several contexts
+    (here on the devices this box has, several contexts per device when it has only one) -- ragged row blocks,
+    ragged stripes inside a block, more contexts than rows"""
+    import ctypes as C
+    lib = nl.load_library()
+    cnt = C.c_int()
+    nl.binding.check(lib.nl_device_count(C.byref(cnt)))
+    w, h, n = 64, 37, 20
+    frames = O.synth_frames(n, 777, w * h)
+    ptrs = (C.c_void_p * n)(*[frames[i].ctypes.data for i in range(n)])
+    wts = weights_for(n)
+    for n_ctx in (1, 2, 3, 5):
+        ctxs = [nl.Context(g % cnt.value) for g in range(n_ctx)]
+        try:
+            arr = (C.c_void_p * n_ctx)(*[c.handle for c in ctxs])
+            for stripes in (1, 3, 50):
+                for mode, name, wv in ((nl.ST_SIGMA, "sigma", None), (nl.ST_WINSOR_SIGMA, "winsor", wts), (nl.ST_MEAN, "mean", None),
+                                       (nl.ST_LINEAR_FIT, "linfit", None)):
+                    out = np.full(w * h, -1.0, np.float32)
+                    cl, ch = C.c_int64(), C.c_int64()
+                    wp = wv.ctypes.data_as(C.POINTER(C.c_float)) if wv is not None else None
+                    nl.binding.check(lib.nl_stack_apply_multi(arr, n_ctx, ptrs, n, w * h, w, stripes, mode, wp, 2.75, 2.75, 0.0,
+                                                              out.ctypes.data_as(C.c_void_p), C.byref(cl), C.byref(ch)))
+                    want = O.stack(frames, name, weights=wv)
+                    assert bits_equal(out, want[0]), (n_ctx, stripes, name, first_mismatch(out, want[0]))
+                    assert (cl.value, ch.value) == want[1:]
+        finally:
+            for c in ctxs:
+                c.close()
+    # h = 2 rows over 5 contexts: three contexts get nothing
+    ctxs = [nl.Context(0) for _ in range(5)]
+    try:
+        arr = (C.c_void_p * 5)(*[c.handle for c in ctxs])
+        out = np.empty(2 * w, np.float32)
+        nl.binding.check(lib.nl_stack_apply_multi(arr, 5, ptrs, n, 2 * w, w, 8, nl.ST_SIGMA, None, 2.75, 2.75, 0.0,
+                                                  out.ctypes.data_as(C.c_void_p), None, None))
+        assert bits_equal(out, O.stack(frames[:, :2 * w], "sigma")[0])
+        rc = lib.nl_stack_apply_multi(arr, 5, ptrs, n, 2 * w, w, 8, 11, None, 2.75, 2.75, 0.0, out.ctypes.data_as(C.c_void_p), None, None)
+        assert rc == nl.binding.NL_E_INVALID and b"invalid stacking mode" in lib.nl_last_error()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_stack_apply_lanes_are_sized_once(ctx):
+    """ragged stripes (rows % n_stripes != 0) run in lanes sized for the largest stripe: repeated calls allocate nothing"""
+    import ctypes as C
+    lib = nl.load_library()
+    w, h, n = 128, 251, 12                         # 251 rows in 2 stripes: 126 + 125
+    frames = O.synth_frames(n, 99, w * h)
+    ptrs = (C.c_void_p * n)(*[frames[i].ctypes.data for i in range(n)])
+    want = O.stack(frames, "sigma")
+    with nl.Context(0) as c:
+        free = []
+        for rep in range(4):
+            out = np.empty(w * h, np.float32)
+            cl, ch = C.c_int64(), C.c_int64()
+            nl.binding.check(lib.nl_stack_apply(c.handle, ptrs, n, w * h, w, 2, nl.ST_SIGMA, None, 2.75, 2.75, 0.0,
+                                                out.ctypes.data_as(C.c_void_p), C.byref(cl), C.byref(ch)))
+            assert bits_equal(out, want[0]) and (cl.value, ch.value) == want[1:]
+            free.append(c.mem_info()[0])
+        assert free[1] == free[2] == free[3], free
+
+
+def test_count_only_runs_and_native_goal_seek(ctx):
+    """a21 in the C ABI: nl_stack_clip_counts_only gives the clip totals of a full run without writing an image, and
+    nl_find_sigmas_and_stack (count-only trials + one stack) ends where the float32 restatement of the reference's
+    commented-out FindSigmasAndStack ends when it is driven by the oracle"""
+    frames = O.synth_frames(40, 5000, 4000)
+    n, p = frames.shape
+    wts = weights_for(n)
+    with nl.StackJob(ctx, n, p) as job:
+        for i in range(n):
+            job.put_frame(i, frames[i])
+        for mode, name, wv in ((nl.ST_SIGMA, "sigma", None), (nl.ST_WINSOR_SIGMA, "winsor", wts), (nl.ST_LINEAR_FIT, "linfit", None),
+                               (nl.ST_MAD_SIGMA, "mad", None), (nl.ST_MEAN, "mean", wts), (nl.ST_MEDIAN, "median", None)):
+            want = O.stack(frames, name, 2.0, 2.5, weights=wv)
+            assert job.clip_counts_only(mode, wv, 2.0, 2.5) == want[1:], name
+        for mode, name, lo, hi in ((nl.ST_SIGMA, "sigma", 1.0, 1.5), (nl.ST_WINSOR_SIGMA, "winsor", 0.5, 2.0),
+                                   (nl.ST_AUTO, "linfit", 2.0, 2.0), (nl.ST_MEDIAN, "median", 1.0, 1.0)):
+            got = job.find_sigmas_and_stack(mode, lo, hi)
+            calls = []
+
+            def oracle_stack(sl, sh):
+                calls.append((sl, sh))
+                return O.stack(frames, name, sl, sh)
+
+            want = nl.find_sigmas_and_stack(oracle_stack, mode, n, p, lo, hi)
+            assert (np.float32(got[3]), np.float32(got[4])) == (np.float32(want[3]), np.float32(want[4])), (name, got[3:], want[3:])
+            assert got[1:3] == want[1:3], name
+            assert bits_equal(got[0], want[0]), (name, first_mismatch(got[0], want[0]))
+            if name != "median":
+                assert got[5] == len(calls)
+
+
+@pytest.mark.parametrize("mode,weighted", [("mean", False), ("mean", True), ("sigma", False)])
+def test_result_pointers_that_are_not_16_byte_aligned(ctx, mode, weighted):
+    """a job of pixels % 4 == 0 whose result (or a peer copy) starts at an odd float: the float4 stores of the mean
+    kernel would fault there, so the launcher must take the scalar path"""
+    frames = O.synth_frames(12, 31, 4096)
+    n, p = frames.shape
+    w = weights_for(n) if weighted else None
+    want = O.stack(frames, mode, weights=w)
+    buf = ctx.dev_alloc(4 * (3 * p + 64))
+    try:
+        with nl.StackJob(ctx, n, p) as job:
+            for i in range(n):
+                job.put_frame(i, frames[i])
+            for off_out, off_peer in ((1, 0), (0, 3), (2, 1)):
+                out, peer = buf + 4 * off_out, buf + 4 * (p + 16 + off_peer)
+                job.run_dev_bcast(MODE_ID[mode], out, [peer], w)
+                ctx.sync()
+                for ptr in (out, peer):
+                    got = np.empty(p, np.float32)
+                    ctx.d2h(got, ptr)
+                    assert bits_equal(got, want[0]), (off_out, off_peer)
+    finally:
+        ctx.dev_free(buf)

@@ -64,3 +64,25 @@ def mode_cases():
         if m in ("mean", "sigma", "winsor"):
             out.append((m, True))
     return out
+
+
+def synth_frames_threaded(n, p0, length, seed=12345):
+    """[n, length] float32 of the synthetic workload (oracle generator), generated with all host threads
+    (ctypes calls release the GIL) -- for the full-size parity tests"""
+    import ctypes as C
+    import threading
+    from oracle import oracle as O
+    lib = O.lib()
+    fp = C.POINTER(C.c_float)
+    frames = np.empty((n, length), dtype=np.float32)
+    cores = os.cpu_count() or 1
+    per = (n + cores - 1) // cores
+
+    def gen(k0, k1):
+        for k in range(k0, k1):
+            lib.nlo_synth_frame(frames[k].ctypes.data_as(fp), p0, length, k, seed)
+
+    th = [threading.Thread(target=gen, args=(k0, min(n, k0 + per))) for k0 in range(0, n, per)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return frames

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="smaller inputs (for ncu)")
     ap.add_argument("--only", default="", help="comma list: mean,mean_w,median,sigma,sigma_w,winsor,winsor_w,mad,linfit,project,fits,bright,prestats,incremental")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--tile-width", default="0", help="force the column kernel's tile width (nl_ctx_set_tuning)")
+    ap.add_argument("--defer-passes", default=None, help="deferral schedule, e.g. 3 or 8,12,16 or 0 (nl_ctx_set_tuning)")
     args = ap.parse_args()
     import torch
     import nightlight_b200 as nl
@@ -33,6 +35,9 @@ def main():
     peak, peak_src = peaks()
     lib = nl.load_library()
     ctx = nl.Context(0)
+    ctx.set_tuning("tile_width", args.tile_width)
+    if args.defer_passes is not None:
+        ctx.set_tuning("defer_passes", args.defer_passes)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -116,7 +121,7 @@ def main():
         job.synth_fill()
         out = torch.empty(pixels, dtype=torch.float32, device=dev)
         ms = timed(lambda: job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=3)
-        report("stack<sigma> n=512 tile=%s" % os.environ.get("NL_TILE_WIDTH", "auto"), "%d x 4096x32" % n, 4.0 * (n + 1) * pixels, ms)
+        report("stack<sigma> n=512 tile=%s" % args.tile_width, "%d x 4096x32" % n, 4.0 * (n + 1) * pixels, ms)
         job.close()
         del out
     if "linfit1024" in only or (not only and not args.quick):
@@ -126,7 +131,7 @@ def main():
         out = torch.empty(pixels, dtype=torch.float32, device=dev)
         for name, mode in (("linfit", nl.ST_LINEAR_FIT), ("sigma", nl.ST_SIGMA)):
             ms = timed(lambda: job.run_dev(mode, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=3)
-            report("stack<%s> n=1024 tile=%s" % (name, os.environ.get("NL_TILE_WIDTH", "auto")), "%d x 8192x8 fp32 (inputs %.2f GiB > L2)" % (n, 4.0 * n * pixels / 2**30),
+            report("stack<%s> n=1024 tile=%s" % (name, args.tile_width), "%d x 8192x8 fp32 (inputs %.2f GiB > L2)" % (n, 4.0 * n * pixels / 2**30),
                    4.0 * (n + 1) * pixels, ms, {"mpx_in_per_s": n * pixels / ms / 1e3})
         job.close()
         del out
@@ -207,10 +212,10 @@ def main():
             ctx.set_numerics(nl.NUMERICS_AMD64)
             # the in-order replay of the float64 chains (taken when neither proof decides), forced for the measurement
             img2 = imgs[0]
-            os.environ["NL_STATS_FORCE_REPLAY"] = "1"
+            ctx.set_tuning("stats_force_replay", "1")
             r0 = ctx.exact_replays()
             ms = timed(lambda: nl.binding.check(lib.nl_stats_dev(ctx.handle, C.c_void_p(img2.data_ptr()), w * h, st)), reps=3, warm=1)
-            os.environ.pop("NL_STATS_FORCE_REPLAY")
+            ctx.set_tuning("stats_force_replay", "0")
             report("stats with both chains replayed in order (worst case)", "%dx%d" % (w, h), 8.0 * w * h, ms,
                    {"exact_replays": ctx.exact_replays() - r0})
             del img2

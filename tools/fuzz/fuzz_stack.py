@@ -18,8 +18,7 @@ for seed in range(300, 380):
 # heavy-tailed, bigger, default schedules and a few odd ones
 from oracle import oracle as O
 for sched in (None, "1", "2,4,6", "5"):
-    if sched is None: os.environ.pop("NL_DEFER_PASSES", None)
-    else: os.environ["NL_DEFER_PASSES"] = sched
+    ctx.set_tuning("defer_passes", sched or "")
     rng = np.random.default_rng(7)
     for n, p in ((256, 32 * 97 + 3), (200, 4096), (33, 5000)):
         fr = (rng.standard_t(1.5, size=(n, p)) * 10 + 100).astype(np.float32)

@@ -15,8 +15,7 @@ cases = mode_cases()
 for seed in range(40):
     rng = np.random.default_rng(1000 + seed)
     sched = rng.choice(["", "1", "2", "3", "1,2,3", "2,5,9", "0"])
-    if sched == "": os.environ.pop("NL_DEFER_PASSES", None)
-    else: os.environ["NL_DEFER_PASSES"] = str(sched)
+    ctx.set_tuning("defer_passes", str(sched))
     n = int(rng.choice([257, 300, 480, 513, 520, 777, 1024, 1100, 2100]))
     p = int(rng.integers(1, 140))
     scale = float(rng.choice([1e-3, 1.0, 50.0]))

@@ -12,8 +12,7 @@ with nl.StackJob(ctx, n, px) as job:
     ctx.sync()
     for mode, name in ((nl.ST_SIGMA, "sigma"), (nl.ST_WINSOR_SIGMA, "winsor"), (nl.ST_LINEAR_FIT, "linfit (StAuto for 64 frames)"), (nl.ST_MEDIAN, "median"), (nl.ST_MEAN, "mean")):
         for sched in ("0", None):
-            if sched is None: os.environ.pop("NL_DEFER_PASSES", None)
-            else: os.environ["NL_DEFER_PASSES"] = sched
+            ctx.set_tuning("defer_passes", sched or "")
             ts = []
             for rep in range(3):
                 ctx.sync(); t0 = time.perf_counter()
