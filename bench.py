@@ -256,6 +256,9 @@ class Env:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             self.dist = dist
         self.ctx = nl.Context(self.local_rank)
+        for kv in [x for x in (args.tune or "").split(",") if x]:      # nl_ctx_set_tuning knobs (A/B measurements)
+            k, v = kv.split("=", 1)
+            self.ctx.set_tuning(k, v.replace(":", ","))
         self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=torch.device("cuda", self.local_rank))
         self.lib = nl.load_library()
 
@@ -925,6 +928,7 @@ def main():
     ap.add_argument("--stack-memory-mb", type=int, default=0, help="c5: memory budget of a batch per GPU (default: 60 %% of the free device memory)")
     ap.add_argument("--clip-perc-low", type=float, default=2.0, help="c5: target percentage of samples clipped on the low side")
     ap.add_argument("--clip-perc-high", type=float, default=2.0)
+    ap.add_argument("--tune", default="", help="k=v,k=v: nl_ctx_set_tuning knobs of the library (A/B measurements; lists with ':')")
     ap.add_argument("--traffic", action="store_true", help="measure the DRAM traffic of one step with ncu -> profiles/traffic_<config>.json")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -202,6 +202,11 @@ int  nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t 
                       int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]);
 int  nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
                           float *dev_tmp, int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]);
+/* BadPixelMap of every frame of a resident stack (frame i at dev_frames + i*frame_stride, 16-byte aligned) in one call:
+ * stats = n_frames x 4, counts = n_frames, frame i's list at host_bpm + i*cap. */
+int  nl_bad_pixel_map_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int64_t len,
+                                int32_t width, float sigma_low, float sigma_high, int32_t *host_bpm, int64_t cap, int64_t *counts,
+                                float *stats);
 /* OpBadPixel.Apply for monochrome frames (internal/ops/pre/preprocess.go:180-191): BadPixelMap, then
  * MedianFilterSparse (badpixels.go:79-85) repairs the listed pixels of host_data in place, one after the other.
  * Returns immediately when either sigma is 0, like the reference.  *removed = number of repaired pixels;
@@ -235,6 +240,13 @@ int  nl_project_scaled(nl_ctx *ctx, const float *host_src, int32_t src_w, int32_
                        int32_t dst_h, const float trans[6], float out_of_bounds, float multiplier, float offset);
 int  nl_project_scaled_dev(nl_ctx *ctx, const float *dev_src, int32_t src_w, int32_t src_h, float *dev_dst, int32_t dst_w,
                            int32_t dst_h, const float trans[6], float out_of_bounds, float multiplier, float offset);
+/* OpAlign over ALL frames of a resident stack in one launch (postprocess.go:142-191 runs Project once per frame from a
+ * pool of goroutines): frame i is read at dev_src + i*src_stride and written at dev_dst + i*dst_stride -- e.g. straight
+ * into slot i of a stack job (nl_stack_frames_dev).  trans = n_frames x 6 floats (Transform2D each); multipliers /
+ * offsets = n_frames floats each (histogram match fused, as in nl_project_scaled) or both NULL. */
+int  nl_project_batch_dev(nl_ctx *ctx, const float *dev_src, int64_t src_stride, int32_t src_w, int32_t src_h, float *dev_dst,
+                          int64_t dst_stride, int32_t dst_w, int32_t dst_h, int32_t n_frames, const float *trans,
+                          float out_of_bounds, const float *multipliers, const float *offsets);
 /* Frame-sharded resample feeding row-sharded stacking.  Resamples one frame like
  * nl_project_scaled_dev (multiplier 1, offset 0 = plain Project) and stores destination rows
  * [stripe_row0[g], stripe_row0[g+1]) at stripe_frames[g] + frame_index * rows_g * dw, i.e. as frame `frame_index`
@@ -273,6 +285,23 @@ int  nl_find_stars(nl_ctx *ctx, const float *host_data, int32_t len, int32_t wid
 int  nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data, int32_t len, int32_t width, float location,
                        float scale, float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev,
                        nl_star *out, int32_t cap, int32_t *count, float *sum_of_shifts, float *avg_hfr);
+
+/* The same for ALL frames of a resident stack (frame i at dev_frames + i*frame_stride), as OpStarDetect runs over a
+ * frame set (preprocess.go:440-465, one goroutine per frame):
+ * nl_find_bright_batch_dev: one read of every frame (candidates go to per-row slots, then into raster order) and two
+ *   host round trips for the whole set; thresholds = n_frames floats; frame i's candidates at host_out + i*cap.
+ * nl_find_stars_batch_dev: that scan, then the sparse per-star steps of every frame on host threads reading
+ *   host_frames[i] (the same pixels).  location, scale, median_diff_stddev, counts, sum_of_shifts, avg_hfr are arrays
+ *   of n_frames entries; frame i's stars at out + i*cap.  seconds_device / seconds_host (may be NULL) report the time
+ *   spent in the device scan and in the host steps. */
+int  nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t len,
+                              int32_t width, const float *thresholds, int32_t radius, nl_star *host_out, int32_t cap,
+                              int32_t *counts);
+int  nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride,
+                             const float *const *host_frames, int32_t len, int32_t width, const float *location,
+                             const float *scale, float star_sig, float bp_sigma, float star_in_out, int32_t radius,
+                             const float *median_diff_stddev, nl_star *out, int32_t cap, int32_t *counts,
+                             float *sum_of_shifts, float *avg_hfr, double *seconds_device, double *seconds_host);
 
 /* ---- synthetic frames (the workload generator, not reference code) --- */
 int  nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64_t count, uint32_t frame, uint32_t seed);

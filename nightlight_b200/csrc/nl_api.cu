@@ -184,6 +184,8 @@ int nl_ctx_set_tuning(nl_ctx *ctx, const char *key, const char *value) {
         ctx->tile_width = w;
         return NL_OK;
     }
+    if (k == "linfit_stream") { ctx->linfit_stream = atoi(v.c_str()); return NL_OK; }
+    if (k == "linfit_stream_ctas") { ctx->linfit_stream_ctas = atoi(v.c_str()); return NL_OK; }
     if (k == "stats_debug") { ctx->stats_debug = atoi(v.c_str()) != 0; return NL_OK; }
     if (k == "stats_force_replay") { ctx->stats_force_replay = atoi(v.c_str()) != 0; return NL_OK; }
     return set_error(NL_E_INVALID, "unknown tuning key '%s'", key);

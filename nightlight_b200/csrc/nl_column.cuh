@@ -773,8 +773,9 @@ NL_HD float reduce_mad(float *g, float *ad, int cur, float sig_lo, float sig_hi,
 template <int S>
 NL_HD float reduce_linfit(float *g, int &cur, int nmax, const float *ramp, float sig_lo, float sig_hi, int &ncl, int &nch,
                           bool sorted = false, int max_iters = 0, bool *pending = nullptr) {
-    // max_iters > 0: stop after that many rejection rounds; *pending tells which columns are not finished.  A column's
-    // state between rounds is its sorted survivors g[0..cur): calling again with sorted = true resumes it.
+    // max_iters > 0: stop after that many rejection rounds (< 0: right after the sort); *pending tells which columns are
+    // not finished.  A column's state between rounds is its sorted survivors g[0..cur): calling again with sorted = true
+    // resumes it.
     if (!sorted) {
 #if defined(__CUDA_ARCH__)
         if (S < 32) {
@@ -788,6 +789,10 @@ NL_HD float reduce_linfit(float *g, int &cur, int nmax, const float *ramp, float
     }
     float mean = 0.0f;
     bool done = cur == 0;
+    if (max_iters < 0) {                                  // sort only: every column with samples is handed on
+        if (pending) *pending = !done;
+        return mean;
+    }
     // sum of the samples in index order: the first chain of MeanStdDev (stats.go:247-250).  After the first
     // round it rides on the compaction of the survivors, which visits them in exactly that order.
     float ysum = 0.0f;

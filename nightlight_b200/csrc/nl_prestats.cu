@@ -778,6 +778,27 @@ int nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_
     return set_error(NL_E_CUDA, "bad-pixel map: list did not fit after growing");
 }
 
+// BadPixelMap of every frame of a resident stack in one call (frame i at dev_frames + i*frame_stride): the frames are
+// processed one after the other on the context's stream -- their float64 statistics decide host-side whether a chain
+// must be replayed -- but the caller crosses the language boundary once.  stats = n_frames x 4, counts = n_frames,
+// host_bpm receives frame i's list at host_bpm + i*cap.
+int nl_bad_pixel_map_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int64_t len, int32_t width,
+                               float sigma_low, float sigma_high, int32_t *host_bpm, int64_t cap, int64_t *counts, float *stats) {
+    NL_REQUIRE(ctx && counts && stats && n_frames >= 0, "bad argument");
+    NL_REQUIRE(dev_frames || n_frames == 0, "NULL frames");
+    NL_REQUIRE(frame_stride % 4 == 0 && ((uintptr_t)dev_frames & 15) == 0, "frames must start on 16 bytes");
+    NL_GUARD(ctx);
+    float *tmp = nullptr;
+    int rc = ensure_frame(ctx, 1, sizeof(float) * (size_t)len, &tmp);
+    if (rc != NL_OK) return rc;
+    for (int i = 0; i < n_frames; i++) {
+        rc = nl_bad_pixel_map_dev(ctx, dev_frames + (size_t)i * frame_stride, len, width, sigma_low, sigma_high, tmp,
+                                  host_bpm ? host_bpm + (size_t)i * cap : nullptr, host_bpm ? cap : 0, counts + i, stats + 4 * i);
+        if (rc != NL_OK) return rc;
+    }
+    return NL_OK;
+}
+
 int nl_bad_pixel_map(nl_ctx *ctx, const float *host_data, int64_t len, int32_t width, float sigma_low, float sigma_high,
                      int32_t *host_bpm, int64_t cap, int64_t *count, float stats[4]) {
     NL_REQUIRE(ctx && host_data && len >= 1, "bad argument");

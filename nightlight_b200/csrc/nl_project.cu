@@ -6,6 +6,8 @@
 // destination pixel.  fp32 in the reference's evaluation order, no FMA contraction.
 #include "nl_internal.h"
 
+#include <vector>
+
 namespace nl {
 
 struct Affine { float a, b, c, d, e, f; };
@@ -67,6 +69,33 @@ __global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ 
 #pragma unroll
     for (int r = 0; r < PR; r++)
         if (row0 + r < dh) __stcs(dst + (size_t)(row0 + r) * dw + col, v[r]);
+}
+
+// All frames of a resident stack in ONE launch (grid.z = frame): frame i is read at src + i*src_stride and written at
+// dst + i*dst_stride (e.g. straight into slot i of a stack job) with its own inverse transform and histogram match.
+struct BatchParam { Affine inv; float mult, offset; int scale; int pad; };
+
+__global__ void __launch_bounds__(256) project_batch_kernel(const float *__restrict__ src, long long src_stride, int sw, int sh,
+                                                            float *__restrict__ dst, long long dst_stride, int dw, int dh,
+                                                            const BatchParam *__restrict__ params, float oob) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row0 = (blockIdx.y * blockDim.y + threadIdx.y) * PR;
+    if (col >= dw || row0 >= dh) return;
+    const BatchParam bp = params[blockIdx.z];
+    const float *s = src + (long long)blockIdx.z * src_stride;
+    float *d = dst + (long long)blockIdx.z * dst_stride;
+    const float x = (float)col, ax = __fmul_rn(bp.inv.a, x), dx = __fmul_rn(bp.inv.d, x);
+    float v[PR];
+    if (bp.scale) {
+#pragma unroll
+        for (int r = 0; r < PR; r++) v[r] = (row0 + r < dh) ? project_pixel<true>(s, sw, sh, bp.inv, ax, dx, row0 + r, oob, bp.mult, bp.offset) : 0.0f;
+    } else {
+#pragma unroll
+        for (int r = 0; r < PR; r++) v[r] = (row0 + r < dh) ? project_pixel<false>(s, sw, sh, bp.inv, ax, dx, row0 + r, oob, 1.0f, 0.0f) : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < PR; r++)
+        if (row0 + r < dh) __stcs(d + (size_t)(row0 + r) * dw + col, v[r]);
 }
 
 // Frame-sharded resample feeding row-sharded stacking: the destination rows of one frame are not
@@ -154,6 +183,44 @@ int nl_project_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, fl
 int nl_project_scaled_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, float *dev_dst, int32_t dw, int32_t dh,
                           const float trans[6], float oob, float multiplier, float offset) {
     return project_launch(ctx, dev_src, sw, sh, dev_dst, dw, dh, trans, oob, true, multiplier, offset);
+}
+
+// OpAlign over all frames of a resident stack (postprocess.go:142-191 runs Project once per frame from a pool of
+// goroutines): n_frames resamples in one launch.  trans = n_frames x 6 floats; multipliers / offsets = n_frames floats
+// each or NULL (no histogram match); a multiplier of 1 with an offset of 0 also means "no match" for that frame.
+int nl_project_batch_dev(nl_ctx *ctx, const float *dev_src, int64_t src_stride, int32_t sw, int32_t sh, float *dev_dst,
+                         int64_t dst_stride, int32_t dw, int32_t dh, int32_t n_frames, const float *trans, float oob,
+                         const float *multipliers, const float *offsets) {
+    NL_REQUIRE(ctx && trans && n_frames >= 0, "bad argument");
+    NL_REQUIRE(sw >= 0 && sh >= 0 && dw >= 0 && dh >= 0, "negative image size");
+    NL_REQUIRE((long long)sw * sh <= 0x7fffffffll && (long long)dw * dh <= 0x7fffffffll, "image larger than int32 pixels (fits.go:40)");
+    NL_REQUIRE(n_frames <= 65535, "more than 65535 frames in one batch");
+    NL_REQUIRE((multipliers == nullptr) == (offsets == nullptr), "multipliers and offsets come together");
+    std::vector<BatchParam> params((size_t)n_frames);
+    for (int i = 0; i < n_frames; i++) {
+        float inv[6];
+        int rc = nl_transform_invert(trans + 6 * i, inv);
+        if (rc != NL_OK) return rc;
+        params[i].inv = Affine{inv[0], inv[1], inv[2], inv[3], inv[4], inv[5]};
+        params[i].mult = multipliers ? multipliers[i] : 1.0f;
+        params[i].offset = offsets ? offsets[i] : 0.0f;
+        params[i].scale = (multipliers && !(multipliers[i] == 1.0f && offsets[i] == 0.0f)) ? 1 : 0;   // d*1 + 0 would turn -0 into +0
+        params[i].pad = 0;
+    }
+    if (n_frames == 0 || dw == 0 || dh == 0) return NL_OK;
+    NL_REQUIRE(dev_dst && (dev_src || sw == 0 || sh == 0), "NULL image pointer");
+    NL_GUARD(ctx);
+    int rc = ensure_scratch(ctx, sizeof(BatchParam) * (size_t)n_frames);
+    if (rc != NL_OK) return rc;
+    NL_CUDA(cudaMemcpyAsync(ctx->scratch, params.data(), sizeof(BatchParam) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));                      // `params` is pageable host memory about to go away
+    dim3 block(PBX, PBY);
+    dim3 grid((dw + block.x - 1) / block.x, (dh + PR * block.y - 1) / (PR * block.y), n_frames);
+    project_batch_kernel<<<grid, block, 0, ctx->stream>>>(dev_src, src_stride, sw, sh, dev_dst, dst_stride, dw, dh,
+                                                         (const BatchParam *)ctx->scratch, oob);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return NL_OK;
 }
 
 int nl_project_scatter_dev(nl_ctx *ctx, const float *dev_src, int32_t sw, int32_t sh, int32_t dw, int32_t dh, const float trans[6],

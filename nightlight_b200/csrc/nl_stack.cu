@@ -386,6 +386,7 @@ static int stack_apply_range(nl_ctx *ctx, const float *const *host_frames, int32
                 lc->defer_override = ctx->defer_override; lc->defer_n = ctx->defer_n;
                 for (int i = 0; i < 8; i++) lc->defer_at[i] = ctx->defer_at[i];
                 lc->tile_width = ctx->tile_width;
+                lc->linfit_stream = ctx->linfit_stream; lc->linfit_stream_ctas = ctx->linfit_stream_ctas;
             }
         }
         if (rc == NL_OK && (lane_px > ctx->lane_px[l] || n_frames != ctx->lane_frames[l] || !ctx->lane_job[l])) {   // (re)size the lane

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
                 else if (MODE == ST_WINSOR) r = reduce_winsor<S, W, IDX>(g, gw, a.weights, c, a.sig_lo, a.sig_hi, ncl, nch, limit, &pending);
                 else r = reduce_linfit<S>(g, c, __reduce_max_sync(0xffffffffu, c), a.ramp, a.sig_lo, a.sig_hi, ncl, nch, sorted, limit, &pending);
                 if (mine) res = r;
-                const unsigned pm = limit > 0 ? __ballot_sync(0xffffffffu, pending) : 0u;
+                const unsigned pm = limit != 0 ? __ballot_sync(0xffffffffu, pending) : 0u;
                 if (pm == 0u) break;
                 // hand the unfinished columns to the pool: consecutive slots for this warp's columns
                 unsigned long long base = 0;
@@ -284,6 +284,414 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
             atomicAdd(a.clip + 0, (unsigned long long)ncl);
             atomicAdd(a.clip + 1, (unsigned long long)nch);
         }
+    }
+}
+
+
+// ---- linear fit, streaming rejection rounds (narrow tiles: more than 256 frames) -----------------------------------
+// The rejection rounds of StackLinearFit (stack.go:849-915) only ever walk a column front to back -- three sequential
+// fp32 chains per round (variance + covariance, mean absolute residual, the survivors' sum) -- so, once a column is
+// SORTED, they need no per-lane dynamic indexing and no shared-memory residency: this kernel streams the sorted columns
+// of a pool from global memory (L2), 32 columns to a warp, lane = column, every load a coalesced row of the pool tile.
+// Rejected samples are not compacted away (that would need a per-lane store index): a bit mask of the surviving
+// samples lives in shared memory ([word][lane], 4 bytes per 32 samples) and every operation of a sample is predicated on
+// its bit; the x coordinate of a sample -- its index among the survivors -- is a running per-lane count.  The
+// arithmetic, operation for operation, is reduce_linfit's (nl_column.cuh).  With no column slab in shared memory the
+// SM holds 16+ warps instead of 7 x 8 lanes: the long columns that need 8-pixel tiles in stack_column_kernel (a quarter
+// of the lanes busy) run with all lanes busy here.
+// Launch r: up to `defer_passes` rounds (0: to the end); unfinished columns are written, compacted, to pool_out and
+// regrouped by the next launch.
+#ifndef NL_LINFIT_STREAM_WARPS
+#define NL_LINFIT_STREAM_WARPS 8
+#endif
+constexpr int LINFIT_STREAM_WARPS = NL_LINFIT_STREAM_WARPS;
+constexpr int LINFIT_POOL_S = 8;           // pool tile width of the streaming linear fit: 8 pixels = one 32-byte sector per sample row
+
+// Sort of the long columns for the streaming linear fit: ONE COLUMN PER WARP, the column in registers.  Lane l holds the
+// R consecutive samples l*R .. l*R+R-1 (32 R >= n_frames; NaNs and the padding enter as +inf and sort to the end, where
+// they are dropped), and the warp runs a bitonic sorting network over the 32 R values: the stages whose partners are
+// less than R apart are compare-exchanges between a lane's own registers (two FMNMX each), the wider ones one shuffle
+// and one FMNMX per sample.  Any correct sort gives the reference's sorted column (qsort.go:26-32 sorts in place; the
+// sorted array is unique up to the order of equal values and signed zeros, which no later sum can see).
+// A warp sorts the 8 adjacent pixels of a tile one after the other -- the 32-byte sectors its scattered loads touch hold
+// exactly those 8 pixels, so every frame sector is fetched from HBM once -- and writes every sorted column, with its
+// pixel and sample count, to slot = pixel of the pool ([tile][sample][8]).
+// compare-exchange across lanes: the lower lane of a pair keeps the smaller value (one compare, one select)
+__device__ __forceinline__ float keep_min_or_max(float v, float o, bool lower) { return ((v > o) == lower) ? o : v; }
+
+// Ascending-only formulation of the bitonic network: the first stage of every merge pairs sample e with its mirror
+// e ^ (k-1), the remaining stages are half-cleaners (e, e ^ s); in all of them the lower index gets the minimum, so
+// the comparators inside a lane are two FMNMX with nothing to decide, and across lanes a shuffle, a compare and a select.
+template <int R>
+__device__ __forceinline__ void bitonic_sort_lane_major(float (&v)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+        if (k <= R) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if ((r & (k >> 1)) == 0) {
+                    const float x = v[r], y = v[r ^ (k - 1)];
+                    v[r] = fminf(x, y);
+                    v[r ^ (k - 1)] = fmaxf(x, y);
+                }
+            }
+        } else {
+            // mirror across lanes: sample (lane, r) meets (lane ^ (k/R - 1), R-1-r)
+            const int lm = k / R - 1;
+            const bool lower = (lane & (k / (2 * R))) == 0;
+#pragma unroll
+            for (int r = 0; r < R / 2; r++) {
+                const float o0 = __shfl_xor_sync(0xffffffffu, v[R - 1 - r], lm);
+                const float o1 = __shfl_xor_sync(0xffffffffu, v[r], lm);
+                v[r] = keep_min_or_max(v[r], o0, lower);
+                v[R - 1 - r] = keep_min_or_max(v[R - 1 - r], o1, lower);
+            }
+        }
+#pragma unroll
+        for (int s = k >> 2; s >= 1; s >>= 1) {
+            if (s >= R) {
+                const int ls = s / R;
+                const bool lower = (lane & ls) == 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) v[r] = keep_min_or_max(v[r], __shfl_xor_sync(0xffffffffu, v[r], ls), lower);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((r & s) == 0) {
+                        const float x = v[r], y = v[r | s];
+                        v[r] = fminf(x, y);
+                        v[r | s] = fmaxf(x, y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- asynchronous staging of pool rows (cp.async, 16 bytes = half a sample row of one 8-pixel pool tile) -----------
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// mask |= BIT when x > y: a compare and one predicated OR with an immediate
+template <unsigned BIT>
+__device__ __forceinline__ void or_bit_if_gt(unsigned &mask, float x, float y) {
+    asm("{\n .reg .pred p;\n setp.gt.f32 p, %1, %2;\n @p or.b32 %0, %0, %3;\n}" : "+r"(mask) : "f"(x), "f"(y), "n"(BIT));
+}
+template <int J>
+struct RejectTests {       // samples J .. 31 of a block: the two rejection tests of StackLinearFit, bits into the masks
+    static __device__ __forceinline__ void run(const float (&v)[32], unsigned w, float slope, float icpt, float lob, float hib,
+                                               float &fi, unsigned &lowm, unsigned &highm) {
+        const float lin = nl_addf(nl_mulf(fi, slope), icpt);
+        or_bit_if_gt<(1u << J)>(lowm, nl_subf(lin, v[J]), lob);        // lin - y > sigmaLow * sigma
+        or_bit_if_gt<(1u << J)>(highm, nl_subf(v[J], lin), hib);       // y - lin > sigmaHigh * sigma
+        if ((w >> J) & 1u) fi += 1.0f;
+        RejectTests<J + 1>::run(v, w, slope, icpt, lob, hib, fi, lowm, highm);
+    }
+};
+template <>
+struct RejectTests<32> {
+    static __device__ __forceinline__ void run(const float (&)[32], unsigned, float, float, float, float, float &, unsigned &, unsigned &) {}
+};
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int LINFIT_SORT_WARPS = 6;        // resident warps per SM (one warp per CTA: all control flow is then CTA-uniform,
+                                            // which lets the compiler treat the warp's shuffles as converged)
+// shared-memory slab of one warp: the tile's 32 R sample rows of 8 pixels, 4 words of padding after every 32 rows (the
+// lanes of a warp then read / write a column's samples l*R + r four to a bank instead of all 32 in one)
+template <int R> struct SortSlab { static constexpr int WORDS = 32 * R * 8 + 4 * R; };
+__device__ __forceinline__ int sort_slab_word(int e, int c) { return e * 8 + c + 4 * (e >> 5); }
+
+template <int R>
+__global__ void __launch_bounds__(32) linfit_sort_kernel(StackArgs a) {
+    constexpr int S = LINFIT_POOL_S;
+    extern __shared__ __align__(128) float sort_smem[];
+    const int lane = threadIdx.x;
+    float *slab = sort_smem;
+    const unsigned slab_addr = smem_u32(slab);
+    const long long warp = blockIdx.x;
+    const long long n_warps = gridDim.x;
+    const int npad = (a.n + 31) & ~31;
+    const long long tiles = (a.pixels + S - 1) / S;
+    if (warp == 0 && lane == 0) *a.pool_out.count = (unsigned long long)a.pixels;      // slot = pixel: every pixel has a column
+    // 16-byte copies need frame rows that start on 16 bytes and whole tiles
+    const bool aligned = (a.stride % 4) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0;
+    for (long long t = warp; t < tiles; t += n_warps) {
+        const long long p0 = t * S;
+        const int cols = (int)((a.pixels - p0) < S ? (a.pixels - p0) : S);
+        // ---- stage the tile: sample row k = the 8 pixels of frame k, one 32-byte sector
+        if (aligned && cols == S) {
+            const float *src = a.frames + p0;
+            for (int q = lane; q < 2 * a.n; q += 32) {
+                const int k = q >> 1, h = q & 1;
+                cp_async16(slab_addr + 4u * (unsigned)sort_slab_word(k, h * 4), src + (long long)k * a.stride + h * 4);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else {
+            for (int q = lane; q < 8 * a.n; q += 32) {
+                const int k = q >> 3, c = q & 7;
+                slab[sort_slab_word(k, c)] = c < cols ? __ldg(a.frames + (long long)k * a.stride + p0 + c) : 0.0f;
+            }
+        }
+        __syncwarp();
+        int my_valid = 0;                                            // lane c < 8: the sample count of column c
+#pragma unroll 1
+        for (int c = 0; c < S; c++) {                                // (a ragged last tile sorts its zero-filled columns too)
+            float v[R];
+            int valid = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int e = lane * R + r;
+                const float x = e < a.n ? slab[sort_slab_word(e, c)] : __int_as_float(0x7fc00000);
+                const bool ok = x == x;
+                valid += ok ? 1 : 0;
+                v[r] = ok ? x : INFINITY;                          // (a real +inf sample equals the padding: either may stay)
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+            bitonic_sort_lane_major<R>(v, lane);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int e = lane * R + r;
+                if (e < npad) slab[sort_slab_word(e, c)] = v[r];
+            }
+            if (lane == c) my_valid = valid;
+        }
+        __syncwarp();
+        // ---- the sorted tile goes out as it came in: whole sectors
+        float *tile_out = a.pool_out.samples + t * ((long long)npad * S);
+        for (int q = lane; q < 2 * npad; q += 32) {
+            const int k = q >> 1, h = q & 1;
+            const float4 x = *reinterpret_cast<const float4 *>(slab + sort_slab_word(k, h * 4));
+            __stcg(reinterpret_cast<float4 *>(tile_out + (long long)k * S + h * 4), x);
+        }
+        if (lane < cols) {
+            a.pool_out.pixel[p0 + lane] = p0 + lane;
+            a.pool_out.cur[p0 + lane] = my_valid;
+        }
+        __syncwarp();
+    }
+}
+
+// A warp's view of its 32 columns: four consecutive pool tiles of 8 pixels ([sample][8] each).  Block b = samples
+// 32b .. 32b+31 of all 32 columns = 32 rows x 4 tiles x 32 bytes; it is copied into a [row][32 lanes] buffer in shared
+// memory by 8 cp.async of 16 bytes per lane (coalesced: whole 32-byte sectors), two buffers deep, so the copy of the
+// next block runs while the lanes work on the current one.  Lane l copies, for i = 0..7, the 16-byte half h = l & 1 of
+// row 4i + (l >> 3) of tile (l & 7) >> 1: source and destination advance by constants from one chunk to the next.
+struct BlockStream {
+    const float *lane_src;          // this lane's chunk 0 of block 0
+    unsigned lane_dst;              // shared-window address of this lane's chunk 0 in buffer 0
+    __device__ __forceinline__ void init(const float *first_tile, int npad, unsigned buf) {
+        const int lane = threadIdx.x & 31;
+        const int lrow = lane >> 3, t = (lane & 7) >> 1, h = lane & 1;
+        lane_src = first_tile + (long long)t * ((long long)npad * 8) + (lrow * 8 + h * 4);
+        lane_dst = buf + (unsigned)(lrow * 128 + t * 32 + h * 16);
+    }
+    __device__ __forceinline__ void issue(int b, int which) const {
+        const float *src = lane_src + (long long)b * 256;
+        const unsigned dst = lane_dst + (unsigned)which * 4096u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) cp_async16(dst + (unsigned)i * 512u, src + i * 32);
+        cp_async_commit();
+    }
+};
+
+// walks the blocks of the warp's columns: f(b, v) gets the 32 samples of block b of THIS lane's column.  A ring of
+// STREAM_DEPTH buffers: the copies of the next STREAM_DEPTH-1 blocks are in flight while the lanes work on one (with few
+// warps per SM -- the columns in flight must fit the L2 -- one block ahead does not cover the L2 latency).
+#ifndef NL_STREAM_DEPTH
+#define NL_STREAM_DEPTH 4
+#endif
+constexpr int STREAM_DEPTH = NL_STREAM_DEPTH;
+template <typename F>
+__device__ __forceinline__ void stream_blocks(const BlockStream &bs, const float *stage, int nblk, F &&f) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 0; d < STREAM_DEPTH - 1; d++) {
+        if (d < nblk) bs.issue(d, d); else cp_async_commit();
+    }
+#pragma unroll 1
+    for (int b = 0; b < nblk; b++) {
+        const int ahead = b + STREAM_DEPTH - 1;
+        if (ahead < nblk) bs.issue(ahead, ahead % STREAM_DEPTH); else cp_async_commit();     // (an empty group keeps the count)
+        cp_async_wait<STREAM_DEPTH - 1>();
+        __syncwarp();
+        const float *src = stage + (b % STREAM_DEPTH) * 1024 + lane;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = src[j * 32];
+        f(b, v);
+        __syncwarp();                                               // the buffer is refilled STREAM_DEPTH-1 blocks later
+    }
+    cp_async_wait<0>();
+}
+
+template <int S>
+__global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel(StackArgs a) {
+    static_assert(S == 8, "the streaming rounds read pools of 8-pixel tiles");
+    extern __shared__ __align__(128) unsigned char stream_smem[];      // per warp: STREAM_DEPTH 4 KiB block buffers, then the survivor masks [word][lane]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npad = (a.n + 31) & ~31;
+    const int nwords = npad >> 5;
+    const size_t per_warp = 4096 * STREAM_DEPTH + (size_t)nwords * 128;
+    float *stage = reinterpret_cast<float *>(stream_smem + (size_t)warp * per_warp);
+    unsigned *alive = reinterpret_cast<unsigned *>(stream_smem + (size_t)warp * per_warp + 4096 * STREAM_DEPTH) + lane;   // word w at alive[w * 32]
+    const unsigned long long cnt = *a.pool_in.count;
+    const long long pool_slots = cnt < (unsigned long long)a.pool_in.cap ? (long long)cnt : a.pool_in.cap;
+    const long long groups = (pool_slots + 31) / 32;
+    int ncl = 0, nch = 0;
+    auto next_group = [&]() {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(a.pool_tile_counter, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    for (long long grp = next_group(); grp < groups; grp = next_group()) {
+        const long long slot = grp * 32 + lane;
+        const bool valid = slot < pool_slots;
+        const long long p = valid ? a.pool_in.pixel[slot] : 0;
+        int cur = valid ? a.pool_in.cur[slot] : 0;
+        const int cur0 = cur;
+        // the warp's four tiles: slots grp*32 .. grp*32+31 (the pool's capacity is a multiple of 32 slots, so all four exist)
+        BlockStream bs;
+        bs.init(a.pool_in.samples + grp * 4 * ((long long)npad * S), npad, smem_u32(stage));
+        const int nblk = (__reduce_max_sync(0xffffffffu, cur) + 31) >> 5;
+        // the survivors' masks, and the sum of the samples in index order (first chain of MeanStdDev, stats.go:247-250)
+        float ysum = 0.0f;
+        stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+            const int rem = cur - b * 32;
+            const unsigned w = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+            alive[b * 32] = w;
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if ((w >> j) & 1u) ysum = nl_addf(ysum, v[j]);
+        });
+        float mean = 0.0f;
+        bool done = cur == 0;
+        bool mine = true, spilled = false;
+        float res = 0.0f;
+        int limit = a.defer_passes;
+        for (;;) {
+            int round = 0;
+            while (__any_sync(0xffffffffu, !done)) {
+                if (limit > 0 && round == limit) {
+                    // a column the last round emptied is not handed on: its next round is mean = 0/0, nothing left to reject
+                    if (!done && cur == 0) { mean = nl_divf(ysum, 0.0f); done = true; }
+                    break;
+                }
+                round++;
+                const int m = done ? 0 : cur;
+                // LinearRegression(xs, ys), stats.go:569-586, xs = 0..m-1: the second pass of MeanStdDev(ys) with the
+                // covariance sum riding on it, each chain in the reference's order
+                const float xm = __ldg(a.ramp + 2 * m), xsd = __ldg(a.ramp + 2 * m + 1);
+                const float fm = (float)m;
+                const float ym = nl_divf(ysum, fm);
+                float yvar = 0.0f, corr = 0.0f, fi = 0.0f;
+                stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                    const unsigned w = done ? 0u : alive[b * 32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if ((w >> j) & 1u) {
+                            const float d = nl_subf(v[j], ym);
+                            yvar = nl_addf(yvar, nl_mulf(d, d));
+                            corr = nl_addf(corr, nl_mulf(nl_subf(fi, xm), d));
+                            fi += 1.0f;
+                        }
+                    }
+                });
+                const float ysd = nl_sqrtf(nl_divf(yvar, fm));
+                corr = nl_divf(corr, nl_mulf(nl_mulf(xsd, ysd), nl_addf(fm, 1.0f)));
+                const float slope = nl_divf(nl_mulf(corr, ysd), xsd);
+                const float icpt = nl_subf(ym, nl_mulf(slope, xm));
+                // mean absolute residual, stack.go:878-886
+                float sigma = 0.0f;
+                fi = 0.0f;
+                stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                    const unsigned w = done ? 0u : alive[b * 32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if ((w >> j) & 1u) {
+                            const float lin = nl_addf(nl_mulf(fi, slope), icpt);
+                            sigma = nl_addf(sigma, fabsf(nl_subf(v[j], lin)));
+                            fi += 1.0f;
+                        }
+                    }
+                });
+                sigma = nl_divf(sigma, fm);
+                // rejection (stack.go:889-909): the rejected samples leave the mask, the survivors' sum rides along.
+                // Branch free: the two tests of a sample set bits of a low and a high mask, counted per block.
+                const float lob = nl_mulf(a.sig_lo, sigma), hib = nl_mulf(a.sig_hi, sigma);
+                float nsum = 0.0f;
+                int left = 0;
+                fi = 0.0f;
+                stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                    const unsigned w = done ? 0u : alive[b * 32];
+                    // (the tests of dead samples set garbage bits, masked below; x only advances over survivors)
+                    unsigned lowm = 0u, highm = 0u;
+                    RejectTests<0>::run(v, w, slope, icpt, lob, hib, fi, lowm, highm);
+                    lowm &= w;
+                    highm &= w & ~lowm;                                              // `else if`: low wins
+                    {
+                        const unsigned ok = w & ~(lowm | highm);
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if ((ok >> j) & 1u) nsum = nl_addf(nsum, v[j]);
+                    }
+                    ncl += __popc(lowm);
+                    nch += __popc(highm);
+                    const unsigned keep = w & ~(lowm | highm);
+                    if (keep != w) alive[b * 32] = keep;
+                    left += __popc(keep);
+                });
+                if (!done) {
+                    mean = ym;
+                    if (left == cur || cur < 3) done = true;          // nothing rejected || len < 3
+                    cur = left;
+                    ysum = nsum;
+                }
+            }
+            const bool pending = !done;
+            if (mine) res = mean;
+            const unsigned pm = limit > 0 ? __ballot_sync(0xffffffffu, pending) : 0u;
+            if (pm == 0u) break;
+            // hand the unfinished columns to the next launch: their survivors, compacted, into consecutive slots
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.pool_out.count, (unsigned long long)__popc(pm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const long long oslot = (long long)base + __popc(pm & ((1u << lane) - 1u));
+            spilled = pending && oslot < a.pool_out.cap;
+            const long long wslot = spilled ? oslot : 0;
+            float *dst = a.pool_out.samples + (wslot / S) * ((long long)npad * S) + (wslot % S);
+            int wpos = 0;
+            stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                const unsigned w = spilled ? alive[b * 32] : 0u;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if ((w >> j) & 1u) { dst[(long long)wpos * S] = v[j]; wpos++; }
+                }
+            });
+            if (spilled) {
+                a.pool_out.pixel[oslot] = p;
+                a.pool_out.cur[oslot] = cur;
+            }
+            // a full pool: the columns that found no slot finish here, the other lanes parked
+            mine = pending && !spilled;
+            if (!__any_sync(0xffffffffu, mine)) break;
+            if (!mine) done = true;
+            limit = 0;
+        }
+        if (valid && !spilled) store_result(a, p, cur0 == 0 ? a.ref_loc : res);     // stack.go:388-397: no samples at all
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ncl += __shfl_xor_sync(0xffffffffu, ncl, o);
+        nch += __shfl_xor_sync(0xffffffffu, nch, o);
+    }
+    if (lane == 0 && (ncl | nch)) {
+        atomicAdd(a.clip + 0, (unsigned long long)ncl);
+        atomicAdd(a.clip + 1, (unsigned long long)nch);
     }
 }
 
@@ -417,8 +825,77 @@ inline bool ensure_pools(nl_stack_job *job, int idx_bytes, const double frac[2],
 
 // One launch, or -- deferral of late passes (see StackArgs) -- launch 0 over the frame stack and one launch per pool
 // generation.
+// Linear fit of long columns (more than 256 frames, up to 1024): launch 0 = linfit_sort_kernel (one column per warp, in
+// registers) hands every sorted column to pool 0; then linfit_rounds_kernel streams the pools, regrouping the unfinished
+// columns between launches (schedule of the linear fit, cumulative rounds).  Pool 0 holds every pixel's column once
+// (+100 % of the frame bytes), pool 1 those that are unfinished after the first rounds.  *done stays false when there is
+// no memory for the pools or the columns are longer than the sort holds: the caller falls back to the in-place kernel.
+inline int launch_linfit_stream(nl_stack_job *job, const StackArgs &args, bool *done) {
+    constexpr int S = LINFIT_POOL_S;
+    *done = false;
+    nl_ctx *ctx = job->ctx;
+    if (ctx->linfit_stream == 0 || job->n > 1024) return NL_OK;       // (the register sort holds 32 x 32 samples)
+    DeferSchedule d = defer_schedule(ST_LINFIT, ctx);
+    if (ctx->defer_override && d.n == 0) return NL_OK;                 // "0": the single-launch kernel was asked for
+    const int nwords = ((job->n + 31) & ~31) >> 5;
+    const size_t smem = (size_t)LINFIT_STREAM_WARPS * (4096 * STREAM_DEPTH + (size_t)nwords * 32 * sizeof(unsigned));
+    if (smem > (size_t)ctx->max_smem_optin) return NL_OK;
+    const double frac[2] = {1.0, 0.85};
+    StackArgs::Pool pools[2];
+    if (!ensure_pools(job, 0, frac, pools) || pools[0].cap < ((job->pixels + 31) & ~31ll)) return NL_OK;
+    if (pools[1].cap < 32) d.n = 0;                                    // no second pool: sort, then one launch to the end
+    auto kern = linfit_rounds_kernel<S>;
+    NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 0;
+    NL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, LINFIT_STREAM_WARPS * 32, smem));
+    if (ctas_per_sm < 1) return NL_OK;
+    if (ctx->linfit_stream_ctas > 0 && ctas_per_sm > ctx->linfit_stream_ctas) ctas_per_sm = ctx->linfit_stream_ctas;
+    const unsigned grid = (unsigned)(ctx->sm_count * ctas_per_sm);
+    StackArgs a2 = args;
+    a2.phase = 0;
+    a2.pool_out = pools[0];
+    a2.pool_out.count = job->clip + 3;
+    {
+        const long long tiles = (args.pixels + S - 1) / S;
+        const bool small = job->n <= 512;
+        const size_t ssmem = (size_t)(small ? SortSlab<16>::WORDS : SortSlab<32>::WORDS) * sizeof(float);
+        long long sgrid = tiles;
+        const long long cap = (long long)ctx->sm_count * LINFIT_SORT_WARPS * (small ? 2 : 1);
+        if (sgrid > cap) sgrid = cap;
+        if (sgrid < 1) sgrid = 1;
+        if (small) {
+            NL_CUDA(cudaFuncSetAttribute(linfit_sort_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            linfit_sort_kernel<16><<<(unsigned)sgrid, 32, ssmem, ctx->stream>>>(a2);
+        } else {
+            NL_CUDA(cudaFuncSetAttribute(linfit_sort_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            linfit_sort_kernel<32><<<(unsigned)sgrid, 32, ssmem, ctx->stream>>>(a2);
+        }
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    for (int r = 1; r <= d.n + 1; r++) {
+        a2.phase = r;
+        a2.defer_passes = r <= d.n ? d.at[r - 1] - (r > 1 ? d.at[r - 2] : 0) : 0;
+        a2.pool_in = pools[(r + 1) & 1];
+        a2.pool_in.count = job->clip + 3 + 2 * (r - 1);
+        a2.pool_tile_counter = job->clip + 4 + 2 * (r - 1);
+        a2.pool_out = pools[r & 1];
+        a2.pool_out.count = job->clip + 3 + 2 * r;
+        kern<<<grid, LINFIT_STREAM_WARPS * 32, smem, ctx->stream>>>(a2);
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    *done = true;
+    return NL_OK;
+}
+
 template <int MODE, bool W, int S, typename IDX>
 inline int launch_deferred(nl_stack_job *job, const StackArgs &args) {
+    if constexpr (MODE == ST_LINFIT && S < 32) {
+        bool done = false;
+        int rc = launch_linfit_stream(job, args, &done);
+        if (rc != NL_OK || done) return rc;
+    }
     if (MODE == ST_SIGMA || MODE == ST_WINSOR || MODE == ST_LINFIT) {
         DeferSchedule d = defer_schedule(MODE, job->ctx);
         // several regrouping launches only pay with many tiles per warp (each launch ends in a tail of half-idle SMs):

@@ -20,6 +20,9 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 namespace nl {
@@ -116,6 +119,119 @@ __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
+}
+
+// ---- all frames of a resident stack at once, ONE read of every frame ------------------------------------------------
+// bright_rows_slots_kernel: the walk of bright_rows_kernel over frame blockIdx.y, writing the row's candidates into the
+// row's own K slots while counting (rows with more than K candidates keep counting; their frame is redone by the
+// two-pass scan).  row_offsets_batch_kernel: exclusive scan of the row counts per frame.  bright_compact_kernel: the
+// slots of every row move to the frame's raster-ordered list.
+constexpr int BRIGHT_SLOTS = 32;
+
+__global__ void __launch_bounds__(256) bright_rows_slots_kernel(const float *__restrict__ frames, long long frame_stride, int len, int width,
+                                                                int rows, const float *__restrict__ thresholds, int radius,
+                                                                int *__restrict__ row_count, nl_star *__restrict__ slots) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (row >= rows) return;
+    const int frame = blockIdx.y;
+    const float threshold = thresholds[frame];
+    const long long row0 = (long long)row * width;
+    const int row_len = (int)min((long long)width, (long long)len - row0);
+    const float *src = frames + (long long)frame * frame_stride + row0;
+    nl_star *my = slots + ((long long)frame * rows + row) * BRIGHT_SLOTS;
+    int count = 0, last_x = 0;
+    float last_v = 0.0f;
+    constexpr int U = 8;
+    for (int x0 = 0; x0 < row_len; x0 += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int x = x0 + u * 32 + lane;
+            v[u] = x < row_len ? __ldcs(src + x) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int x = x0 + u * 32 + lane;
+            unsigned hits = __ballot_sync(0xffffffffu, x < row_len && v[u] > threshold);
+            while (hits) {
+                const int b = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float hv = __shfl_sync(0xffffffffu, v[u], b);
+                const int hx = x0 + u * 32 + b;
+                if (count > 0 && last_x >= hx - radius) {            // findstars.go:113-123
+                    if (last_v >= hv) continue;
+                } else {
+                    count++;
+                }
+                last_x = hx; last_v = hv;
+                if (lane == 0 && count <= BRIGHT_SLOTS) {
+                    nl_star st;
+                    st.index = (int)(row0 + hx); st.value = hv; st.x = (float)hx; st.y = (float)row;
+                    st.mass = hv; st.hfr = 1.0f;
+                    my[count - 1] = st;
+                }
+            }
+        }
+    }
+    if (lane == 0) row_count[(long long)frame * rows + row] = count;
+}
+
+__global__ void __launch_bounds__(1024) row_offsets_batch_kernel(const int *__restrict__ row_count, int *__restrict__ row_offset, int rows,
+                                                                 int *__restrict__ totals, int *__restrict__ overflow) {
+    // one CTA per frame: exclusive scan of its row counts; totals[frame] = candidates, overflow[frame] = rows beyond their slots
+    __shared__ int warp_sums[32];
+    __shared__ int carry, over;
+    const int *rc = row_count + (long long)blockIdx.x * rows;
+    int *ro = row_offset + (long long)blockIdx.x * rows;
+    if (threadIdx.x == 0) { carry = 0; over = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < rows; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = i < rows ? rc[i] : 0;
+        if (c > BRIGHT_SLOTS) atomicAdd(&over, 1);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = carry + warp_sums[warp] + incl - c;
+        if (i < rows) ro[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[blockIdx.x] = carry; overflow[blockIdx.x] = over; }
+}
+
+__global__ void __launch_bounds__(256) bright_compact_kernel(const nl_star *__restrict__ slots, const int *__restrict__ row_count,
+                                                             const int *__restrict__ row_offset, int rows, nl_star *__restrict__ list,
+                                                             long long list_stride) {
+    // one warp per row: lane i moves candidate i of the row to the frame's list (frames with overflowing rows are redone)
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (row >= rows) return;
+    const long long fr = (long long)blockIdx.y * rows + row;
+    const int c = row_count[fr];
+    if (lane < c && lane < BRIGHT_SLOTS) {
+        const long long dst = (long long)row_offset[fr] + lane;
+        if (dst < list_stride) list[(long long)blockIdx.y * list_stride + dst] = slots[fr * BRIGHT_SLOTS + lane];
+    }
 }
 
 int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total) {
@@ -399,6 +515,23 @@ static int calc_and_filter_hfr(nl_star *stars, int n, const float *data, int32_t
     return remaining;
 }
 
+// the sparse per-star steps of FindStars (findstars.go:66-99) on `n` raster-ordered candidates; returns the star count
+static int find_stars_sparse(nl_star *stars, int n, const float *host_data, int32_t len, int32_t width, float location, float scale,
+                             float star_sig, float bp_sigma, float star_in_out, int32_t radius, float median_diff_stddev, nl_star *out,
+                             int32_t cap, float *sum_of_shifts, float *avg_hfr) {
+    int m = n;
+    *sum_of_shifts = 0.0f; *avg_hfr = 0.0f;
+    if (bp_sigma > 0) m = reject_bad_pixels(stars, m, host_data, len, width, bp_sigma, median_diff_stddev);
+    qsort_stars_desc(stars, m);
+    m = filter_out_overlaps(stars, m, width, len / width, radius);
+    *sum_of_shifts = shift_to_center_of_mass(stars, m, host_data, len, width, location + scale * star_sig * 0.5f, radius);
+    qsort_stars_desc(stars, m);
+    m = filter_out_overlaps(stars, m, width, len / width, radius);
+    m = calc_and_filter_hfr(stars, m, host_data, len, width, (float)radius, location, star_in_out, avg_hfr);
+    for (int i = 0; i < m && i < cap; i++) out[i] = stars[i];
+    return m;
+}
+
 }  // namespace nl
 
 using namespace nl;
@@ -450,16 +583,131 @@ int nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data
         int rc = bright_scan(ctx, dev_data, len, width, threshold, radius, 0x7fffffff, &stars, nullptr, &n);
         if (rc != NL_OK) return rc;
     }
-    int m = n;
-    if (bp_sigma > 0) m = reject_bad_pixels(stars.data(), m, host_data, len, width, bp_sigma, median_diff_stddev);
-    qsort_stars_desc(stars.data(), m);
-    m = filter_out_overlaps(stars.data(), m, width, len / width, radius);
-    *sum_of_shifts = shift_to_center_of_mass(stars.data(), m, host_data, len, width, location + scale * star_sig * 0.5f, radius);
-    qsort_stars_desc(stars.data(), m);
-    m = filter_out_overlaps(stars.data(), m, width, len / width, radius);
-    m = calc_and_filter_hfr(stars.data(), m, host_data, len, width, (float)radius, location, star_in_out, avg_hfr);
-    for (int i = 0; i < m && i < cap; i++) out[i] = stars[i];
-    *count = m;
+    *count = find_stars_sparse(stars.data(), n, host_data, len, width, location, scale, star_sig, bp_sigma, star_in_out, radius,
+                               median_diff_stddev, out, cap, sum_of_shifts, avg_hfr);
+    return NL_OK;
+}
+
+// findBrightPixels of ALL frames of a resident stack (frame i at dev_frames + i*frame_stride) with one read of every
+// frame and two host round trips in total: per-row slots, scan of the row counts, compaction into raster order.
+// thresholds = n_frames floats.  host_out receives frame i's candidates at host_out + i*cap (the first min(count, cap));
+// counts[i] = candidates found in frame i.
+int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t len, int32_t width,
+                             const float *thresholds, int32_t radius, nl_star *host_out, int32_t cap, int32_t *counts) {
+    NL_REQUIRE(ctx && counts && thresholds && n_frames >= 0, "bad argument");
+    NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(host_out || cap == 0, "out is NULL");
+    NL_REQUIRE(dev_frames || len == 0, "data is NULL");
+    for (int i = 0; i < n_frames; i++) counts[i] = 0;
+    if (len == 0 || n_frames == 0) return NL_OK;
+    NL_REQUIRE(n_frames <= 65535, "more than 65535 frames in one batch");
+    NL_GUARD(ctx);
+    const int rows = (len + width - 1) / width;
+    const size_t fr = (size_t)n_frames * rows;
+    // scratch: row counts | row offsets | thresholds | totals | overflow ; list: the row slots
+    const size_t ints = 2 * fr + 3 * (size_t)n_frames;
+    int rc = ensure_scratch(ctx, (ints * sizeof(int) + 255) & ~(size_t)255);
+    if (rc != NL_OK) return rc;
+    int *row_count = (int *)ctx->scratch, *row_offset = row_count + fr;
+    float *dthr = (float *)(row_offset + fr);
+    int *totals = (int *)(dthr + n_frames), *overflow = totals + n_frames;
+    const size_t slot_bytes = fr * BRIGHT_SLOTS * sizeof(nl_star);
+    if (ctx->list_bytes < slot_bytes) {
+        if (ctx->list) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFree(ctx->list)); ctx->list = nullptr; ctx->list_bytes = 0; }
+        NL_CUDA(cudaMalloc(&ctx->list, slot_bytes));
+        ctx->list_bytes = slot_bytes;
+    }
+    nl_star *slots = (nl_star *)ctx->list;
+    NL_CUDA(cudaMemcpyAsync(dthr, thresholds, sizeof(float) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 256, wpc = threads / 32;
+    dim3 grid((unsigned)((rows + wpc - 1) / wpc), (unsigned)n_frames);
+    bright_rows_slots_kernel<<<grid, threads, 0, ctx->stream>>>(dev_frames, frame_stride, len, width, rows, dthr, radius, row_count, slots);
+    NL_CUDA(cudaGetLastError());
+    row_offsets_batch_kernel<<<(unsigned)n_frames, 1024, 0, ctx->stream>>>(row_count, row_offset, rows, totals, overflow);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    std::vector<int> host_tot(2 * (size_t)n_frames);
+    NL_CUDA(cudaMemcpyAsync(host_tot.data(), totals, 2 * sizeof(int) * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));                       // round trip 1: how many candidates per frame
+    int max_keep = 0;
+    for (int i = 0; i < n_frames; i++) {
+        counts[i] = host_tot[i];
+        const int keep = host_tot[i] < cap ? host_tot[i] : cap;
+        if (host_tot[n_frames + i] == 0 && keep > max_keep) max_keep = keep;
+    }
+    if (max_keep > 0) {
+        // the compacted lists: a second device buffer, then one copy per frame into the caller's array
+        nl_star *dev_list = nullptr;
+        const size_t list_bytes = (size_t)n_frames * max_keep * sizeof(nl_star);
+        NL_CUDA(cudaMalloc(&dev_list, list_bytes));
+        bright_compact_kernel<<<grid, threads, 0, ctx->stream>>>(slots, row_count, row_offset, rows, dev_list, max_keep);
+        cudaError_t e = cudaGetLastError();
+        ctx->launches++;
+        for (int i = 0; i < n_frames && e == cudaSuccess; i++) {
+            const int keep = host_tot[i] < cap ? host_tot[i] : cap;
+            if (host_tot[n_frames + i] == 0 && keep > 0)
+                e = cudaMemcpyAsync(host_out + (size_t)i * cap, dev_list + (size_t)i * max_keep, sizeof(nl_star) * (size_t)keep,
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // round trip 2: the candidates
+        cudaFree(dev_list);
+        if (e != cudaSuccess) return cuda_fail(e, "candidate lists");
+    }
+    // frames with a row beyond its slots (dense star fields, hot columns): the two-pass scan of that frame
+    for (int i = 0; i < n_frames; i++) {
+        if (host_tot[n_frames + i] == 0) continue;
+        int n = 0;
+        rc = bright_scan(ctx, dev_frames + (size_t)i * frame_stride, len, width, thresholds[i], radius, cap, nullptr,
+                         host_out + (size_t)i * cap, &n);
+        if (rc != NL_OK) return rc;
+        counts[i] = n;
+    }
+    return NL_OK;
+}
+
+// FindStars over all frames of a resident stack: one batched scan on the device, then the sparse per-star steps of
+// every frame on host threads (they read the host copies of the frames, host_frames[i]).  Per-frame inputs and outputs
+// are arrays of n_frames entries; out receives frame i's stars at out + i*cap.
+int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, const float *const *host_frames,
+                            int32_t len, int32_t width, const float *location, const float *scale, float star_sig, float bp_sigma,
+                            float star_in_out, int32_t radius, const float *median_diff_stddev, nl_star *out, int32_t cap,
+                            int32_t *counts, float *sum_of_shifts, float *avg_hfr, double *seconds_device, double *seconds_host) {
+    NL_REQUIRE(ctx && counts && sum_of_shifts && avg_hfr && location && scale && host_frames, "NULL argument");
+    NL_REQUIRE(n_frames >= 0 && len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(bp_sigma <= 0 || median_diff_stddev, "median_diff_stddev is needed when bp_sigma > 0");
+    std::vector<float> thr((size_t)n_frames);
+    for (int i = 0; i < n_frames; i++) thr[i] = location[i] + scale[i] * star_sig;            // findstars.go:61
+    // every candidate is needed (the filters follow): size the per-frame list generously, redo if a frame has more
+    int scan_cap = cap > 65536 ? cap : 65536;
+    std::vector<nl_star> cand;
+    std::vector<int32_t> n_cand((size_t)n_frames);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        cand.resize((size_t)n_frames * scan_cap);
+        int rc = nl_find_bright_batch_dev(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, cand.data(), scan_cap,
+                                          n_cand.data());
+        if (rc != NL_OK) return rc;
+        int most = 0;
+        for (int i = 0; i < n_frames; i++) most = n_cand[i] > most ? n_cand[i] : most;
+        if (most <= scan_cap) break;
+        scan_cap = most;
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, (unsigned)n_frames));
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&]() {
+            for (int i = next++; i < n_frames; i = next++)
+                counts[i] = find_stars_sparse(cand.data() + (size_t)i * scan_cap, n_cand[i], host_frames[i], len, width, location[i], scale[i],
+                                              star_sig, bp_sigma, star_in_out, radius, median_diff_stddev ? median_diff_stddev[i] : 0.0f,
+                                              out + (size_t)i * cap, cap, sum_of_shifts + i, avg_hfr + i);
+        });
+    for (auto &t : th) t.join();
+    const auto t2 = std::chrono::steady_clock::now();
+    if (seconds_device) *seconds_device = std::chrono::duration<double>(t1 - t0).count();
+    if (seconds_host) *seconds_host = std::chrono::duration<double>(t2 - t1).count();
     return NL_OK;
 }
 

@@ -76,4 +76,4 @@ def tuning(ctx):
 
     yield set_
     for key in used:
-        ctx.set_tuning(key, "" if key == "defer_passes" else "0")
+        ctx.set_tuning(key, {"defer_passes": "", "linfit_stream": "1"}.get(key, "0"))

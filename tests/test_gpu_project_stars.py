@@ -308,3 +308,130 @@ def test_project_scatter_into_stripe_jobs(ctx):
         ctx.dev_free(src_dev)
         for j in jobs:
             j.close()
+
+
+def _resident(ctx, frames):
+    """frames [n, px] -> a stack job holding them (device), plus the device base pointer and stride"""
+    n, px = frames.shape
+    job = nl.StackJob(ctx, n, px)
+    for i in range(n):
+        job.put_frame(i, frames[i])
+    ctx.sync()
+    base, stride = job.frames_dev
+    return job, base, stride
+
+
+def test_batched_resample_of_a_resident_stack(ctx):
+    """nl_project_batch_dev: all frames in one launch, each with its own transform (and histogram match), written
+    straight into the slots of a second stack job -- equal to the per-frame oracle, then stacked"""
+    import ctypes as C
+    lib = nl.load_library()
+    w, h, n = 333, 257, 7
+    rng = np.random.default_rng(42)
+    frames = (rng.standard_normal((n, w * h)) * 50 + 500).astype(np.float32)
+    trans = np.zeros((n, 6), np.float32)
+    for k in range(n):
+        th = np.deg2rad(rng.uniform(-2, 2))
+        trans[k] = [np.cos(th), -np.sin(th), rng.uniform(-9, 9), np.sin(th), np.cos(th), rng.uniform(-9, 9)]
+    mult = rng.uniform(0.9, 1.1, n).astype(np.float32)
+    off = rng.uniform(-5, 5, n).astype(np.float32)
+    mult[2], off[2] = 1.0, 0.0                          # "no match" for one frame
+    fp = C.POINTER(C.c_float)
+    src_job, sbase, sstride = _resident(ctx, frames)
+    with src_job, nl.StackJob(ctx, n, w * h) as dst_job:
+        dbase, dstride = dst_job.frames_dev
+        for use_match in (False, True):
+            nl.binding.check(lib.nl_project_batch_dev(ctx.handle, C.c_void_p(sbase), sstride, w, h, C.c_void_p(dbase), dstride, w, h, n,
+                                                      trans.ctypes.data_as(fp), float("nan"),
+                                                      mult.ctypes.data_as(fp) if use_match else None,
+                                                      off.ctypes.data_as(fp) if use_match else None))
+            ctx.sync()
+            aligned = []
+            for k in range(n):
+                got = np.empty(w * h, np.float32)
+                ctx.d2h(got, dbase + 4 * k * dstride)
+                src = frames[k]
+                if use_match and not (mult[k] == 1.0 and off[k] == 0.0):
+                    src = (src * mult[k]).astype(np.float32) + off[k]            # MatchHistogram, then Project
+                want = O.project(src.astype(np.float32), w, h, w, h, trans[k], np.float32(np.nan))
+                assert bits_equal(got, want), (use_match, k, first_mismatch(got, want))
+                aligned.append(want)
+            res, cl, ch = dst_job.run(nl.ST_SIGMA)
+            want = O.stack(np.stack(aligned), "sigma")
+            assert bits_equal(res, want[0]) and (cl, ch) == want[1:]
+    bad = trans.copy()
+    bad[3] = [1, 2, 0, 2, 4, 0]
+    rc = lib.nl_project_batch_dev(ctx.handle, C.c_void_p(sbase), sstride, w, h, C.c_void_p(sbase), sstride, w, h, n,
+                                  bad.ctypes.data_as(fp), 0.0, None, None)
+    assert rc == nl.binding.NL_E_SINGULAR
+
+
+def test_batched_star_scan_one_read_per_frame(ctx):
+    """nl_find_bright_batch_dev / nl_find_stars_batch_dev over the frames of a resident stack: per-row slots + scan +
+    compaction equal the oracle's raster-order lists; a frame with a row of more than 32 candidates takes the
+    two-pass scan; the sparse steps on host threads give the oracle's stars"""
+    import ctypes as C
+    lib = nl.load_library()
+    w, h, n = 640, 300, 6
+    frames = np.stack([star_field(w, h, 60, seed=100 + k) for k in range(n)])
+    frames[3].reshape(h, w)[17, ::9] += 4000.0          # 72 isolated hits in one row (radius 4): beyond the 32 slots
+    radius = 4
+    thr = np.array([130.0 + k for k in range(n)], np.float32)
+    job, base, stride = _resident(ctx, frames)
+    with job:
+        cap = 20000
+        out = np.zeros((n, cap), dtype=nl.STAR_DTYPE)
+        counts = np.zeros(n, np.int32)
+        nl.binding.check(lib.nl_find_bright_batch_dev(ctx.handle, C.c_void_p(base), n, stride, w * h, w, thr.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      radius, out.ctypes.data_as(C.c_void_p), cap, counts.ctypes.data_as(C.POINTER(C.c_int32))))
+        for k in range(n):
+            want = O.find_bright_pixels(frames[k], w, float(thr[k]), radius)
+            assert counts[k] == len(want) and len(want) > 20, (k, counts[k], len(want))
+            assert out[k, :counts[k]].tobytes() == want.tobytes(), k
+        # truncated lists still count
+        small = np.zeros((n, 5), dtype=nl.STAR_DTYPE)
+        nl.binding.check(lib.nl_find_bright_batch_dev(ctx.handle, C.c_void_p(base), n, stride, w * h, w, thr.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      radius, small.ctypes.data_as(C.c_void_p), 5, counts.ctypes.data_as(C.POINTER(C.c_int32))))
+        for k in range(n):
+            want = O.find_bright_pixels(frames[k], w, float(thr[k]), radius)
+            assert counts[k] == len(want) and small[k].tobytes() == want[:5].tobytes()
+        # the whole FindStars
+        loc = np.full(n, 100.0, np.float32)
+        scale = np.array([3.0 + 0.1 * k for k in range(n)], np.float32)
+        mds = np.full(n, 4.0, np.float32)
+        stars = np.zeros((n, 4000), dtype=nl.STAR_DTYPE)
+        sos, hfr = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        ptrs = (C.c_void_p * n)(*[frames[k].ctypes.data for k in range(n)])
+        td, thost = C.c_double(), C.c_double()
+        fp = C.POINTER(C.c_float)
+        for bp in (0.0, 5.0):
+            nl.binding.check(lib.nl_find_stars_batch_dev(ctx.handle, C.c_void_p(base), n, stride, ptrs, w * h, w, loc.ctypes.data_as(fp),
+                                                         scale.ctypes.data_as(fp), 15.0, bp, 1.4, 16, mds.ctypes.data_as(fp),
+                                                         stars.ctypes.data_as(C.c_void_p), 4000, counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                         sos.ctypes.data_as(fp), hfr.ctypes.data_as(fp), C.byref(td), C.byref(thost)))
+            for k in range(n):
+                want = O.find_stars(frames[k], w, 100.0, float(scale[k]), 15.0, bp, 1.4, 16, 4.0)
+                assert counts[k] == len(want[0]) and counts[k] > 5, (bp, k)
+                assert stars[k, :counts[k]].tobytes() == want[0].tobytes(), (bp, k)
+                assert bits_equal([sos[k], hfr[k]], [want[1], want[2]])
+            assert td.value > 0 and thost.value > 0
+
+
+def test_batched_bad_pixel_map(ctx):
+    import ctypes as C
+    lib = nl.load_library()
+    w, h, n = 200, 96, 4
+    frames = np.stack([star_field(w, h, 10, seed=7 + k, hot=30) for k in range(n)])
+    job, base, stride = _resident(ctx, frames)
+    with job:
+        cap = 500
+        bpm = np.zeros((n, cap), np.int32)
+        counts = np.zeros(n, np.int64)
+        st = np.zeros((n, 4), np.float32)
+        nl.binding.check(lib.nl_bad_pixel_map_batch_dev(ctx.handle, C.c_void_p(base), n, stride, w * h, w, 3.0, 5.0,
+                                                        bpm.ctypes.data_as(C.POINTER(C.c_int32)), cap, counts.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                        st.ctypes.data_as(C.POINTER(C.c_float))))
+        for k in range(n):
+            want_bpm, want_st, _ = O.bad_pixel_map(frames[k], w, 3.0, 5.0)
+            assert counts[k] == want_bpm.size and np.array_equal(bpm[k, :counts[k]], want_bpm)
+            assert np.array_equal(st[k].view(np.uint32), want_st.view(np.uint32))

@@ -516,3 +516,22 @@ def test_result_pointers_that_are_not_16_byte_aligned(ctx, mode, weighted):
                     assert bits_equal(got, want[0]), (off_out, off_peer)
     finally:
         ctx.dev_free(buf)
+
+
+@pytest.mark.parametrize("stream", ["1", "0"])
+@pytest.mark.parametrize("n,p", [(300, 8 * 40 + 3), (1024, 8 * 70 + 1), (2100, 37)])
+def test_linear_fit_long_columns_streaming_rounds_and_in_place(ctx, tuning, stream, n, p):
+    """more than 256 frames: the linear fit sorts every column in the column kernel and streams the rejection rounds
+    from a pool (linfit_rounds_kernel, survivors as bit masks) -- or, with the tuning switched off, runs them in
+    place; both equal the oracle bit for bit, with heavy tails (many rounds), NaNs, an empty and a one-sample column"""
+    tuning("linfit_stream", stream)
+    rng = np.random.default_rng(n + p)
+    frames = (rng.standard_t(2.5, size=(n, p)) * 30 + 700).astype(np.float32)
+    frames[rng.random((n, p)) < 0.01] = np.nan
+    frames[:, 2] = np.nan
+    frames[1:, 5] = np.nan
+    frames[:, 9] = 3.25                                 # constant column: sigma 0
+    check_against_oracle(ctx, frames, "linfit", False, 2.0, 2.5, ref_loc=9.0)
+    check_against_oracle(ctx, frames, "linfit", False, 0.8, 0.8)
+    frames2 = O.synth_frames(n, 31 * n, p)
+    check_against_oracle(ctx, frames2, "linfit", False)

@@ -1,0 +1,270 @@
+"""bench.py --config c3: BASELINE.json configs[2] as one measured pipeline on one GPU.
+
+    star detection (OpStarDetect / FindStars) -> [alignment: host, out of scope, the transforms are inputs] ->
+    bilinear resample (OpAlign / Image.Project) -> stack (OpStack, StAuto -> linear fit for 64 frames)
+
+over 64 frames of 6000x4000 fp32 that are resident in HBM, through the batched C-ABI entry points
+(nl_bad_pixel_map_batch_dev, nl_find_stars_batch_dev, nl_project_batch_dev, nl_stack_run_dev).  Reference:
+internal/ops/pre/preprocess.go:440-465, internal/star/findstars.go:59-100, internal/ops/post/postprocess.go:142-191,
+internal/fits/project.go:26-76, internal/ops/stack/stack.go:115-227.
+
+The frames are a synthetic star field (Gaussian blobs at hashed positions, flat background, Gaussian noise, a few hot
+pixels) rendered on the host once per frame at the frame's own affine pose; the poses are what the alignment would find.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, N = 6000, 4000, 64
+BACKGROUND, NOISE = 1000.0, 12.0
+STAR_SIG, BP_SIGMA, IN_OUT, RADIUS = 15.0, 5.0, 1.4, 16
+METRIC = "Mpixels/s through star-detect + resample + stack (input samples N*P/t; 64 x 6000x4000 fp32, linear-fit stack)"
+
+
+def poses(n, seed=7):
+    """Transform2D of every frame (frame -> reference), small rotations and shifts like a night of tracking drift"""
+    rng = np.random.default_rng(seed)
+    t = np.zeros((n, 6), np.float32)
+    for k in range(n):
+        th = np.deg2rad(rng.uniform(-0.4, 0.4)) if k else 0.0
+        dx, dy = (rng.uniform(-25, 25), rng.uniform(-25, 25)) if k else (0.0, 0.0)
+        t[k] = [np.cos(th), -np.sin(th), dx, np.sin(th), np.cos(th), dy]
+    return t
+
+
+def render_frame(k, trans, stars, w=W, h=H):
+    """frame k: the star list seen through the inverse of its pose, plus background, noise and hot pixels"""
+    rng = np.random.default_rng(1000 + k)
+    img = rng.standard_normal((h, w), dtype=np.float32)
+    img *= np.float32(NOISE)
+    img += np.float32(BACKGROUND)
+    a, b, c, d, e, f = [float(x) for x in trans]
+    det = a * e - b * d
+    for (x, y, amp, s) in stars:
+        # reference position (x, y) = T(frame position): frame position = T^-1
+        fx = (e * (x - c) - b * (y - f)) / det
+        fy = (-d * (x - c) + a * (y - f)) / det
+        x0, x1, y0, y1 = int(fx) - 12, int(fx) + 13, int(fy) - 12, int(fy) + 13
+        if x0 < 0 or y0 < 0 or x1 > w or y1 > h:
+            continue
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        img[y0:y1, x0:x1] += (amp * np.exp(-((xx - fx) ** 2 + (yy - fy) ** 2) / (2 * s * s))).astype(np.float32)
+    hot = rng.integers(0, w * h, 300)
+    img.reshape(-1)[hot] += np.float32(8000.0)
+    return img.reshape(-1)
+
+
+def star_list(n_stars, seed=3, w=W, h=H):
+    rng = np.random.default_rng(seed)
+    return [(rng.uniform(40, w - 40), rng.uniform(40, h - 40), float(np.exp(rng.uniform(np.log(150), np.log(30000)))),
+             rng.uniform(1.2, 2.8)) for _ in range(n_stars)]
+
+
+def render_all(n, trans, stars, out, w=W, h=H):
+    cores = os.cpu_count() or 1
+
+    def work(k0):
+        for k in range(k0, n, cores):
+            out[k] = render_frame(k, trans[k], stars, w, h)
+
+    th = [threading.Thread(target=work, args=(k0,)) for k0 in range(min(cores, n))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+
+
+def run_c3(args):
+    import torch
+    import nightlight_b200 as nl
+    from bench import ClockSampler, peaks, source_hash, UNIT
+
+    w, h, n = W, H, N
+    if args.rows:                       # smaller frames for quick checks: --rows = frame height
+        h = args.rows
+    px = w * h
+    lib = nl.load_library()
+    torch.cuda.set_device(0)
+    ctx = nl.Context(0)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", 0))
+    fp = C.POINTER(C.c_float)
+
+    # ---- the frame set in pinned host memory
+    t0 = time.perf_counter()
+    host = C.c_void_p()
+    nl.binding.check(lib.nl_host_alloc_pinned(4 * n * px, C.byref(host)))
+    frames = np.ctypeslib.as_array(C.cast(host, fp), shape=(n, px))
+    trans = poses(n)
+    stars = star_list(2500 * h // H + 50, w=w, h=h)
+    render_all(n, trans, stars, frames, w, h)
+    gen_s = time.perf_counter() - t0
+
+    raw = ctx.dev_alloc(4 * n * px)                      # the frames as loaded (after calibration), resident
+    job = nl.StackJob(ctx, n, px)                        # the aligned frames, resident
+    jbase, jstride = job.frames_dev
+    out_dev = ctx.dev_alloc(4 * px)
+    host_out = np.empty(px, np.float32)
+    loc = np.full(n, BACKGROUND, np.float32)             # Stats.Location / Scale: randomized estimators in the reference, inputs here
+    scale = np.full(n, NOISE, np.float32)
+    cap = 20000
+    found = np.zeros((n, cap), dtype=nl.STAR_DTYPE)
+    counts = np.zeros(n, np.int32)
+    sos, hfr = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    bcounts = np.zeros(n, np.int64)
+    bstats = np.zeros((n, 4), np.float32)
+    ptrs = (C.c_void_p * n)(*[host.value + 4 * k * px for k in range(n)])
+    mode = lib.nl_auto_select_mode(n)                    # StAuto: linear fit from 25 frames up
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def rec(e):
+        with torch.cuda.stream(ext):
+            e.record()
+
+    def upload():
+        nl.binding.check(lib.nl_memcpy_h2d(ctx.handle, C.c_void_p(raw), host, 4 * n * px))
+
+    def pipeline(timers):
+        """device-resident pipeline; timers: dict of lists (ms)"""
+        t = time.perf_counter()
+        nl.binding.check(lib.nl_bad_pixel_map_batch_dev(ctx.handle, C.c_void_p(raw), n, px, px, w, 3.0, 5.0, None, 0,
+                                                        bcounts.ctypes.data_as(C.POINTER(C.c_int64)), bstats.ctypes.data_as(fp)))
+        t1 = time.perf_counter()
+        mds = np.ascontiguousarray(bstats[:, 3])
+        td, thost = C.c_double(), C.c_double()
+        nl.binding.check(lib.nl_find_stars_batch_dev(ctx.handle, C.c_void_p(raw), n, px, ptrs, px, w, loc.ctypes.data_as(fp),
+                                                     scale.ctypes.data_as(fp), STAR_SIG, BP_SIGMA, IN_OUT, RADIUS, mds.ctypes.data_as(fp),
+                                                     found.ctypes.data_as(C.c_void_p), cap, counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     sos.ctypes.data_as(fp), hfr.ctypes.data_as(fp), C.byref(td), C.byref(thost)))
+        t2 = time.perf_counter()
+        e0, e1, e2 = ev(), ev(), ev()
+        rec(e0)
+        nl.binding.check(lib.nl_project_batch_dev(ctx.handle, C.c_void_p(raw), px, w, h, C.c_void_p(jbase), jstride, w, h, n,
+                                                  trans.ctypes.data_as(fp), float("nan"), None, None))
+        rec(e1)
+        job.run_dev(mode, out_dev, None, 2.75, 2.75, 0.0)
+        rec(e2)
+        ctx.sync()
+        t3 = time.perf_counter()
+        timers["badpixel_map_ms"].append((t1 - t) * 1e3)
+        timers["detect_device_ms"].append(td.value * 1e3)
+        timers["detect_host_ms"].append(thost.value * 1e3)
+        timers["detect_ms"].append((t2 - t1) * 1e3)
+        timers["resample_ms"].append(e0.elapsed_time(e1))
+        timers["stack_ms"].append(e1.elapsed_time(e2))
+        timers["total_ms"].append((t3 - t) * 1e3)
+
+    upload()
+    ctx.sync()
+    names = ["badpixel_map_ms", "detect_device_ms", "detect_host_ms", "detect_ms", "resample_ms", "stack_ms", "total_ms"]
+    warm = {k: [] for k in names}
+    for _ in range(max(3, args.warmup) if not args.rows else 1):
+        pipeline(warm)
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = ctx.launch_count
+    timers = {k: [] for k in names}
+    steps = args.steps
+    for _ in range(steps):
+        pipeline(timers)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    med = {k: float(np.median(v)) for k, v in timers.items()}
+    clip = job.clip_counts()
+    value = n * px / (med["total_ms"] * 1e-3) / 1e6
+
+    # ---- end to end: upload of the frame set, the pipeline, download of the stacked image
+    e2e_ms = []
+    for _ in range(max(1, min(steps, args.e2e_steps))):
+        t = time.perf_counter()
+        upload()
+        pipeline({k: [] for k in names})
+        ctx.d2h(host_out, out_dev)
+        e2e_ms.append((time.perf_counter() - t) * 1e3)
+    e2e = {"value": n * px / (float(np.median(e2e_ms)) * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 4 * n * px,
+           "d2h_bytes_per_step": 4 * px + n * (24 * int(counts.max()) + 16), "ms_per_step": float(np.median(e2e_ms)),
+           "steps": len(e2e_ms), "host_memory": "pinned",
+           "api": "nl_memcpy_h2d of the frame set, nl_bad_pixel_map_batch_dev, nl_find_stars_batch_dev, nl_project_batch_dev, "
+                  "nl_stack_run_dev, download of the stacked image"}
+
+    # ---- parity and CPU baseline on a bounded sample (the oracle = restatement of the Go code)
+    parity, cpu = {}, None
+    if not args.no_cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        k = 1
+        t = time.perf_counter()
+        want = O.find_stars(frames[k], w, BACKGROUND, NOISE, STAR_SIG, BP_SIGMA, IN_OUT, RADIUS, float(bstats[k, 3]))
+        cpu_detect = time.perf_counter() - t
+        stars_ok = counts[k] == len(want[0]) and found[k, :counts[k]].tobytes() == want[0].tobytes()
+        t = time.perf_counter()
+        wantp = O.project(frames[k], w, h, w, h, trans[k], np.float32(np.nan))
+        cpu_project = time.perf_counter() - t
+        gotp = np.empty(px, np.float32)
+        ctx.d2h(gotp, jbase + 4 * k * jstride)
+        gn, wn = np.isnan(gotp), np.isnan(wantp)
+        proj_ok = bool(np.array_equal(gn, wn) and np.array_equal(gotp.view(np.uint32)[~gn], wantp.view(np.uint32)[~wn]))
+        t = time.perf_counter()
+        _, st_want, _ = O.bad_pixel_map(frames[k], w, 3.0, 5.0)
+        cpu_bpm = time.perf_counter() - t
+        bpm_ok = bool(np.array_equal(st_want.view(np.uint32), bstats[k].view(np.uint32)))
+        # the stack: the first rows of the aligned frames as the GPU produced them, through the CPU linear fit
+        srows = min(64, h)
+        spx = srows * w
+        al = np.empty((n, spx), np.float32)
+        for i in range(n):
+            ctx.d2h(al[i], jbase + 4 * i * jstride)
+        t = time.perf_counter()
+        sw_, cl_, ch_ = O.stack(al, mode, 2.75, 2.75, threads=cores)
+        cpu_stack = time.perf_counter() - t
+        got = np.empty(spx, np.float32)
+        ctx.d2h(got, out_dev)
+        gn, wn = np.isnan(got), np.isnan(sw_)
+        stack_ok = bool(np.array_equal(gn, wn) and np.array_equal(got.view(np.uint32)[~gn], sw_.view(np.uint32)[~wn]))
+        parity = {"frame_checked": k, "stars_bit_exact": bool(stars_ok), "stars": int(counts[k]), "resample_bit_exact": proj_ok,
+                  "median_diff_stats_bit_exact": bpm_ok, "stack_rows_checked": srows, "stack_bit_exact": stack_ok}
+        if not (stars_ok and proj_ok and bpm_ok and stack_ok):
+            raise SystemExit("c3 parity failure: %s" % json.dumps(parity))
+        # extrapolation: the per-frame stages run one frame per core (the reference's goroutine per frame), the stack on all cores
+        rounds = (n + cores - 1) // cores
+        cpu_total = (cpu_bpm + cpu_detect + cpu_project) * rounds + cpu_stack * (h / srows)
+        cpu = {"value": n * px / cpu_total / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "bad-pixel map %.2f s, FindStars %.2f s, Project %.2f s on one frame (one thread each; x %d rounds of %d "
+                         "frames in parallel), linear-fit stack of %d rows %.2f s on %d threads (x %d for the image)" % (
+                             cpu_bpm, cpu_detect, cpu_project, rounds, cores, srows, cpu_stack, cores, h // srows)}
+
+    peak, peak_src = peaks()
+    algo = 4.0 * (n + 1) * px
+    roofline = {"bound": "hbm", "achieved": algo / (med["stack_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo / (med["stack_ms"] * 1e-3) / 1e9 / peak, "traffic": None,
+                "kernel": "stack_column_kernel<linfit> (sort + rejection rounds, unfinished columns regrouped between launches)",
+                "kernel_ms": med["stack_ms"], "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
+                "resample": {"achieved": 8.0 * n * px / (med["resample_ms"] * 1e-3) / 1e9, "frac": 8.0 * n * px / (med["resample_ms"] * 1e-3) / 1e9 / peak,
+                             "algorithmic_bytes": 8.0 * n * px, "kernel": "project_batch_kernel (one launch, 64 frames)"},
+                "detect_scan": {"achieved": 4.0 * n * px / (med["detect_device_ms"] * 1e-3) / 1e9,
+                                "frac": 4.0 * n * px / (med["detect_device_ms"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": 4.0 * n * px,
+                                "kernel": "bright_rows_slots_kernel + row_offsets_batch_kernel + bright_compact_kernel (whole call incl. two host round trips)"}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": med["total_ms"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "star detection (bad-pixel statistics + FindStars) + bilinear resample + StAuto (linear fit) stack of %d x %dx%d fp32 "
+                               "frames resident in HBM; alignment transforms are inputs (host step, out of scope)" % (n, w, h),
+                   "config": "c3", "n_frames": n, "width": w, "height": h, "stages_ms": med, "stars_per_frame": [int(counts.min()), int(counts.max())],
+                   "bad_pixels_per_frame": [int(bcounts.min()), int(bcounts.max())], "clipped": list(clip), "mode": int(mode),
+                   "l2": "64 frames of %.0f MB each, every stage larger than L2" % (4 * px / 1e6), "host_generation_s": gen_s,
+                   "parity": parity, "source_hash": source_hash()},
+        "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches,
+    }
+    print(json.dumps(line))
+    ctx.dev_free(raw)
+    ctx.dev_free(out_dev)
+    job.close()
+    lib.nl_host_free_pinned(host)
+    ctx.close()
+    return 0

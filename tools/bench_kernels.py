@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="smaller inputs (for ncu)")
     ap.add_argument("--only", default="", help="comma list: mean,mean_w,median,sigma,sigma_w,winsor,winsor_w,mad,linfit,project,fits,bright,prestats,incremental")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--tune", default="", help="k=v,k=v: nl_ctx_set_tuning knobs (A/B measurements)")
     ap.add_argument("--tile-width", default="0", help="force the column kernel's tile width (nl_ctx_set_tuning)")
     ap.add_argument("--defer-passes", default=None, help="deferral schedule, e.g. 3 or 8,12,16 or 0 (nl_ctx_set_tuning)")
     args = ap.parse_args()
@@ -38,6 +39,9 @@ def main():
     ctx.set_tuning("tile_width", args.tile_width)
     if args.defer_passes is not None:
         ctx.set_tuning("defer_passes", args.defer_passes)
+    for kv in [x for x in args.tune.split(",") if x]:
+        k, v = kv.split("=", 1)
+        ctx.set_tuning(k, v.replace(":", ","))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -122,6 +126,17 @@ def main():
         out = torch.empty(pixels, dtype=torch.float32, device=dev)
         ms = timed(lambda: job.run_dev(nl.ST_SIGMA, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=3)
         report("stack<sigma> n=512 tile=%s" % args.tile_width, "%d x 4096x32" % n, 4.0 * (n + 1) * pixels, ms)
+        job.close()
+        del out
+    if "linfit1024big" in only:
+        # BASELINE configs[3] depth on a 128-row stripe (1 M pixels, 4 GiB): enough columns to fill the GPU
+        n, pixels = 1024, 8192 * 128
+        job = nl.StackJob(ctx, n, pixels)
+        job.synth_fill()
+        out = torch.empty(pixels, dtype=torch.float32, device=dev)
+        ms = timed(lambda: job.run_dev(nl.ST_LINEAR_FIT, out.data_ptr(), None, 2.75, 2.75, 0.0), flush_l2=False, reps=args.reps, warm=1)
+        report("stack<linfit> n=1024, 1M px", "%d x 8192x128 fp32 (inputs %.2f GiB > L2)" % (n, 4.0 * n * pixels / 2**30),
+               4.0 * (n + 1) * pixels, ms, {"mpx_in_per_s": n * pixels / ms / 1e3})
         job.close()
         del out
     if "linfit1024" in only or (not only and not args.quick):
