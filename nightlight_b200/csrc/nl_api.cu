@@ -125,6 +125,7 @@ int nl_ctx_destroy(nl_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->list) cudaFree(ctx->list);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->batch_pinned) cudaFreeHost(ctx->batch_pinned);
     for (int k = 0; k < 2; k++)
         if (ctx->frame[k]) cudaFree(ctx->frame[k]);
     cudaStreamDestroy(ctx->stream);

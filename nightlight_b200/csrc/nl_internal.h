@@ -29,6 +29,9 @@ struct nl_ctx {
     void *pinned = nullptr;          // mapped pinned host memory: the star scan writes its count and candidates straight into it
     void *pinned_dev = nullptr;      // (its device address)
     size_t pinned_bytes = 0;
+    void *batch_pinned = nullptr;    // mapped pinned host memory of the batched star scan: [frame][stride] candidate records
+    void *batch_pinned_dev = nullptr;
+    size_t batch_pinned_bytes = 0;
     void *list = nullptr;            // candidate list of the star scan (kept apart from `scratch`, which holds the row offsets)
     size_t list_bytes = 0;
     // nl_stack_apply keeps its two stripe lanes (context + job + result buffer each) between calls:

@@ -85,7 +85,9 @@ __device__ __forceinline__ void store_result(const StackArgs &a, long long p, fl
 
 // ---- order-statistics modes ------------------------------------------------------------------
 // shared-memory bytes per column slot: the fp32 samples, the MAD scratch column, and (weighted
-// modes) the frame index of every sample
+// modes) the frame index of every sample.  (Measured: moving the index column to an L2-resident scratch in global
+// memory gives the weighted modes the seven warps per SM of the unweighted ones, but the clip loop's dependent
+// load/store pairs then wait on L2: sigma_w 10.4 -> 14.9 ms, winsor_w 14.9 -> 15.4 ms per 512-row stripe.  Rejected.)
 template <int MODE, bool W, typename IDX> struct SlotBytes {
     static constexpr int value = 4 * (MODE == ST_MAD ? 2 : 1) + (W ? (int)sizeof(IDX) : 0);
 };
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) stack_column_kernel(StackArgs a, const __
 // Launch r: up to `defer_passes` rounds (0: to the end); unfinished columns are written, compacted, to pool_out and
 // regrouped by the next launch.
 #ifndef NL_LINFIT_STREAM_WARPS
-#define NL_LINFIT_STREAM_WARPS 8
+#define NL_LINFIT_STREAM_WARPS 6
 #endif
 constexpr int LINFIT_STREAM_WARPS = NL_LINFIT_STREAM_WARPS;
 constexpr int LINFIT_POOL_S = 8;           // pool tile width of the streaming linear fit: 8 pixels = one 32-byte sector per sample row
@@ -396,49 +398,50 @@ struct RejectTests<32> {
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int LINFIT_SORT_WARPS = 6;        // resident warps per SM (one warp per CTA: all control flow is then CTA-uniform,
-                                            // which lets the compiler treat the warp's shuffles as converged)
-// shared-memory slab of one warp: the tile's 32 R sample rows of 8 pixels, 4 words of padding after every 32 rows (the
+constexpr int LINFIT_SORT_CTAS = 6;         // resident CTAs per SM (shared memory: one tile slab each)
+constexpr int LINFIT_SORT_WARPS = 2;        // warps per CTA: they stage one tile together and sort four of its columns each
+                                            // (all control flow is CTA-uniform, so the compiler treats the shuffles as converged)
+// shared-memory slab of a CTA: the tile's 32 R sample rows of 8 pixels, 4 words of padding after every 32 rows (the
 // lanes of a warp then read / write a column's samples l*R + r four to a bank instead of all 32 in one)
 template <int R> struct SortSlab { static constexpr int WORDS = 32 * R * 8 + 4 * R; };
 __device__ __forceinline__ int sort_slab_word(int e, int c) { return e * 8 + c + 4 * (e >> 5); }
 
 template <int R>
-__global__ void __launch_bounds__(32) linfit_sort_kernel(StackArgs a) {
+__global__ void __launch_bounds__(LINFIT_SORT_WARPS * 32) linfit_sort_kernel(StackArgs a) {
     constexpr int S = LINFIT_POOL_S;
+    constexpr int T = LINFIT_SORT_WARPS * 32;
     extern __shared__ __align__(128) float sort_smem[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, tid = threadIdx.x;
     float *slab = sort_smem;
     const unsigned slab_addr = smem_u32(slab);
-    const long long warp = blockIdx.x;
-    const long long n_warps = gridDim.x;
     const int npad = (a.n + 31) & ~31;
     const long long tiles = (a.pixels + S - 1) / S;
-    if (warp == 0 && lane == 0) *a.pool_out.count = (unsigned long long)a.pixels;      // slot = pixel: every pixel has a column
+    if (blockIdx.x == 0 && tid == 0) *a.pool_out.count = (unsigned long long)a.pixels;      // slot = pixel: every pixel has a column
     // 16-byte copies need frame rows that start on 16 bytes and whole tiles
     const bool aligned = (a.stride % 4) == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 15) == 0;
-    for (long long t = warp; t < tiles; t += n_warps) {
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const long long p0 = t * S;
         const int cols = (int)((a.pixels - p0) < S ? (a.pixels - p0) : S);
         // ---- stage the tile: sample row k = the 8 pixels of frame k, one 32-byte sector
         if (aligned && cols == S) {
             const float *src = a.frames + p0;
-            for (int q = lane; q < 2 * a.n; q += 32) {
+            for (int q = tid; q < 2 * a.n; q += T) {
                 const int k = q >> 1, h = q & 1;
                 cp_async16(slab_addr + 4u * (unsigned)sort_slab_word(k, h * 4), src + (long long)k * a.stride + h * 4);
             }
             cp_async_commit();
             cp_async_wait<0>();
         } else {
-            for (int q = lane; q < 8 * a.n; q += 32) {
+            for (int q = tid; q < 8 * a.n; q += T) {
                 const int k = q >> 3, c = q & 7;
                 slab[sort_slab_word(k, c)] = c < cols ? __ldg(a.frames + (long long)k * a.stride + p0 + c) : 0.0f;
             }
         }
-        __syncwarp();
-        int my_valid = 0;                                            // lane c < 8: the sample count of column c
+        __syncthreads();
+        int my_valid = 0;                                            // lane i < 4: the sample count of this warp's column i
 #pragma unroll 1
-        for (int c = 0; c < S; c++) {                                // (a ragged last tile sorts its zero-filled columns too)
+        for (int i = 0; i < S / LINFIT_SORT_WARPS; i++) {            // (a ragged last tile sorts its zero-filled columns too)
+            const int c = wic * (S / LINFIT_SORT_WARPS) + i;
             float v[R];
             int valid = 0;
 #pragma unroll
@@ -457,21 +460,22 @@ __global__ void __launch_bounds__(32) linfit_sort_kernel(StackArgs a) {
                 const int e = lane * R + r;
                 if (e < npad) slab[sort_slab_word(e, c)] = v[r];
             }
-            if (lane == c) my_valid = valid;
+            if (lane == i) my_valid = valid;
         }
-        __syncwarp();
+        __syncthreads();
         // ---- the sorted tile goes out as it came in: whole sectors
         float *tile_out = a.pool_out.samples + t * ((long long)npad * S);
-        for (int q = lane; q < 2 * npad; q += 32) {
+        for (int q = tid; q < 2 * npad; q += T) {
             const int k = q >> 1, h = q & 1;
             const float4 x = *reinterpret_cast<const float4 *>(slab + sort_slab_word(k, h * 4));
             __stcg(reinterpret_cast<float4 *>(tile_out + (long long)k * S + h * 4), x);
         }
-        if (lane < cols) {
-            a.pool_out.pixel[p0 + lane] = p0 + lane;
-            a.pool_out.cur[p0 + lane] = my_valid;
+        const int c_mine = wic * (S / LINFIT_SORT_WARPS) + lane;
+        if (lane < S / LINFIT_SORT_WARPS && c_mine < cols) {
+            a.pool_out.pixel[p0 + c_mine] = p0 + c_mine;
+            a.pool_out.cur[p0 + c_mine] = my_valid;
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -860,15 +864,15 @@ inline int launch_linfit_stream(nl_stack_job *job, const StackArgs &args, bool *
         const bool small = job->n <= 512;
         const size_t ssmem = (size_t)(small ? SortSlab<16>::WORDS : SortSlab<32>::WORDS) * sizeof(float);
         long long sgrid = tiles;
-        const long long cap = (long long)ctx->sm_count * LINFIT_SORT_WARPS * (small ? 2 : 1);
+        const long long cap = (long long)ctx->sm_count * LINFIT_SORT_CTAS * (small ? 2 : 1);
         if (sgrid > cap) sgrid = cap;
         if (sgrid < 1) sgrid = 1;
         if (small) {
             NL_CUDA(cudaFuncSetAttribute(linfit_sort_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-            linfit_sort_kernel<16><<<(unsigned)sgrid, 32, ssmem, ctx->stream>>>(a2);
+            linfit_sort_kernel<16><<<(unsigned)sgrid, LINFIT_SORT_WARPS * 32, ssmem, ctx->stream>>>(a2);
         } else {
             NL_CUDA(cudaFuncSetAttribute(linfit_sort_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-            linfit_sort_kernel<32><<<(unsigned)sgrid, 32, ssmem, ctx->stream>>>(a2);
+            linfit_sort_kernel<32><<<(unsigned)sgrid, LINFIT_SORT_WARPS * 32, ssmem, ctx->stream>>>(a2);
         }
         NL_CUDA(cudaGetLastError());
         ctx->launches++;

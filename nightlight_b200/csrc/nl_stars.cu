@@ -588,23 +588,19 @@ int nl_find_stars_dev(nl_ctx *ctx, const float *dev_data, const float *host_data
     return NL_OK;
 }
 
+}  // extern "C"
+
+namespace nl {
+
 // findBrightPixels of ALL frames of a resident stack (frame i at dev_frames + i*frame_stride) with one read of every
-// frame and two host round trips in total: per-row slots, scan of the row counts, compaction into raster order.
-// thresholds = n_frames floats.  host_out receives frame i's candidates at host_out + i*cap (the first min(count, cap));
-// counts[i] = candidates found in frame i.
-int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t len, int32_t width,
-                             const float *thresholds, int32_t radius, nl_star *host_out, int32_t cap, int32_t *counts) {
-    NL_REQUIRE(ctx && counts && thresholds && n_frames >= 0, "bad argument");
-    NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
-    NL_REQUIRE(host_out || cap == 0, "out is NULL");
-    NL_REQUIRE(dev_frames || len == 0, "data is NULL");
-    for (int i = 0; i < n_frames; i++) counts[i] = 0;
-    if (len == 0 || n_frames == 0) return NL_OK;
-    NL_REQUIRE(n_frames <= 65535, "more than 65535 frames in one batch");
-    NL_GUARD(ctx);
+// frame and two host round trips in total: per-row slots, scan of the row counts, compaction into raster order straight
+// into mapped pinned host memory.  On return frame i's first min(counts[i], keep_cap) candidates are at *list + i * *stride
+// (host memory owned by the context, valid until the next batched scan).
+static int bright_scan_batch(nl_ctx *ctx, const float *dev_frames, int n_frames, long long frame_stride, int len, int width,
+                             const float *thresholds, int radius, int keep_cap, nl_star **list, long long *stride, int32_t *counts) {
     const int rows = (len + width - 1) / width;
     const size_t fr = (size_t)n_frames * rows;
-    // scratch: row counts | row offsets | thresholds | totals | overflow ; list: the row slots
+    // scratch: row counts | row offsets | thresholds | totals | overflow ; ctx->list: the row slots
     const size_t ints = 2 * fr + 3 * (size_t)n_frames;
     int rc = ensure_scratch(ctx, (ints * sizeof(int) + 255) & ~(size_t)255);
     if (rc != NL_OK) return rc;
@@ -618,7 +614,20 @@ int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fra
         ctx->list_bytes = slot_bytes;
     }
     nl_star *slots = (nl_star *)ctx->list;
-    NL_CUDA(cudaMemcpyAsync(dthr, thresholds, sizeof(float) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    auto ensure_batch_pinned = [&](size_t bytes) -> int {
+        if (ctx->batch_pinned_bytes >= bytes) return NL_OK;
+        if (ctx->batch_pinned) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFreeHost(ctx->batch_pinned)); ctx->batch_pinned = nullptr; ctx->batch_pinned_bytes = 0; }
+        NL_CUDA(cudaHostAlloc(&ctx->batch_pinned, bytes, cudaHostAllocMapped));
+        NL_CUDA(cudaHostGetDevicePointer(&ctx->batch_pinned_dev, ctx->batch_pinned, 0));
+        ctx->batch_pinned_bytes = bytes;
+        return NL_OK;
+    };
+    const size_t head = (2 * sizeof(int) * (size_t)n_frames + sizeof(float) * (size_t)n_frames + 255) & ~(size_t)255;   // totals | overflow | thresholds
+    rc = ensure_batch_pinned(head + sizeof(nl_star) * (size_t)n_frames * 4096);
+    if (rc != NL_OK) return rc;
+    memcpy((char *)ctx->batch_pinned + 2 * sizeof(int) * (size_t)n_frames, thresholds, sizeof(float) * (size_t)n_frames);
+    NL_CUDA(cudaMemcpyAsync(dthr, (char *)ctx->batch_pinned + 2 * sizeof(int) * (size_t)n_frames, sizeof(float) * (size_t)n_frames,
+                            cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256, wpc = threads / 32;
     dim3 grid((unsigned)((rows + wpc - 1) / wpc), (unsigned)n_frames);
     bright_rows_slots_kernel<<<grid, threads, 0, ctx->stream>>>(dev_frames, frame_stride, len, width, rows, dthr, radius, row_count, slots);
@@ -626,72 +635,96 @@ int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fra
     row_offsets_batch_kernel<<<(unsigned)n_frames, 1024, 0, ctx->stream>>>(row_count, row_offset, rows, totals, overflow);
     NL_CUDA(cudaGetLastError());
     ctx->launches += 2;
-    std::vector<int> host_tot(2 * (size_t)n_frames);
-    NL_CUDA(cudaMemcpyAsync(host_tot.data(), totals, 2 * sizeof(int) * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    NL_CUDA(cudaMemcpyAsync(ctx->batch_pinned, totals, 2 * sizeof(int) * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
     NL_CUDA(cudaStreamSynchronize(ctx->stream));                       // round trip 1: how many candidates per frame
-    int max_keep = 0;
+    std::vector<int> host_tot(2 * (size_t)n_frames);
+    memcpy(host_tot.data(), ctx->batch_pinned, 2 * sizeof(int) * (size_t)n_frames);
+    int max_keep = 1;
     for (int i = 0; i < n_frames; i++) {
         counts[i] = host_tot[i];
-        const int keep = host_tot[i] < cap ? host_tot[i] : cap;
-        if (host_tot[n_frames + i] == 0 && keep > max_keep) max_keep = keep;
+        const int keep = host_tot[i] < keep_cap ? host_tot[i] : keep_cap;
+        if (keep > max_keep) max_keep = keep;
     }
-    if (max_keep > 0) {
-        // the compacted lists: a second device buffer, then one copy per frame into the caller's array
-        nl_star *dev_list = nullptr;
-        const size_t list_bytes = (size_t)n_frames * max_keep * sizeof(nl_star);
-        NL_CUDA(cudaMalloc(&dev_list, list_bytes));
-        bright_compact_kernel<<<grid, threads, 0, ctx->stream>>>(slots, row_count, row_offset, rows, dev_list, max_keep);
-        cudaError_t e = cudaGetLastError();
-        ctx->launches++;
-        for (int i = 0; i < n_frames && e == cudaSuccess; i++) {
-            const int keep = host_tot[i] < cap ? host_tot[i] : cap;
-            if (host_tot[n_frames + i] == 0 && keep > 0)
-                e = cudaMemcpyAsync(host_out + (size_t)i * cap, dev_list + (size_t)i * max_keep, sizeof(nl_star) * (size_t)keep,
-                                    cudaMemcpyDeviceToHost, ctx->stream);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // round trip 2: the candidates
-        cudaFree(dev_list);
-        if (e != cudaSuccess) return cuda_fail(e, "candidate lists");
-    }
+    rc = ensure_batch_pinned(head + sizeof(nl_star) * (size_t)n_frames * max_keep);
+    if (rc != NL_OK) return rc;
+    nl_star *host_list = (nl_star *)((char *)ctx->batch_pinned + head);
+    nl_star *dev_list = (nl_star *)((char *)ctx->batch_pinned_dev + head);
+    bright_compact_kernel<<<grid, threads, 0, ctx->stream>>>(slots, row_count, row_offset, rows, dev_list, max_keep);
+    NL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));                       // round trip 2: the candidates have landed in host memory
     // frames with a row beyond its slots (dense star fields, hot columns): the two-pass scan of that frame
     for (int i = 0; i < n_frames; i++) {
         if (host_tot[n_frames + i] == 0) continue;
         int n = 0;
-        rc = bright_scan(ctx, dev_frames + (size_t)i * frame_stride, len, width, thresholds[i], radius, cap, nullptr,
-                         host_out + (size_t)i * cap, &n);
+        rc = bright_scan(ctx, dev_frames + (size_t)i * frame_stride, len, width, thresholds[i], radius, max_keep, nullptr,
+                         host_list + (size_t)i * max_keep, &n);
         if (rc != NL_OK) return rc;
+        if (n > max_keep && max_keep < keep_cap) {
+            // (the recount found more than the slots let the first pass see: grow the lists and redo the whole batch)
+            return bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thresholds, radius, keep_cap, list, stride, counts);
+        }
         counts[i] = n;
+    }
+    *list = host_list;
+    *stride = max_keep;
+    return NL_OK;
+}
+
+}  // namespace nl
+
+extern "C" {
+
+// findBrightPixels of all frames of a resident stack; host_out receives frame i's candidates at host_out + i*cap (the
+// first min(count, cap)); counts[i] = candidates found in frame i.
+int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t len, int32_t width,
+                             const float *thresholds, int32_t radius, nl_star *host_out, int32_t cap, int32_t *counts) {
+    NL_REQUIRE(ctx && counts && thresholds && n_frames >= 0, "bad argument");
+    NL_REQUIRE(len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(host_out || cap == 0, "out is NULL");
+    NL_REQUIRE(dev_frames || len == 0, "data is NULL");
+    for (int i = 0; i < n_frames; i++) counts[i] = 0;
+    if (len == 0 || n_frames == 0) return NL_OK;
+    NL_REQUIRE(n_frames <= 65535, "more than 65535 frames in one batch");
+    NL_GUARD(ctx);
+    nl_star *list = nullptr;
+    long long stride = 0;
+    int rc = bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thresholds, radius, cap, &list, &stride, counts);
+    if (rc != NL_OK) return rc;
+    for (int i = 0; i < n_frames; i++) {
+        const int keep = counts[i] < cap ? counts[i] : cap;
+        if (keep > 0) memcpy(host_out + (size_t)i * cap, list + (size_t)i * stride, sizeof(nl_star) * (size_t)keep);
     }
     return NL_OK;
 }
 
 // FindStars over all frames of a resident stack: one batched scan on the device, then the sparse per-star steps of
-// every frame on host threads (they read the host copies of the frames, host_frames[i]).  Per-frame inputs and outputs
-// are arrays of n_frames entries; out receives frame i's stars at out + i*cap.
+// every frame on host threads (they read the host copies of the frames, host_frames[i]) working in place on the
+// candidate lists the scan left in pinned host memory.  Per-frame inputs and outputs are arrays of n_frames entries;
+// out receives frame i's stars at out + i*cap.
 int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, const float *const *host_frames,
                             int32_t len, int32_t width, const float *location, const float *scale, float star_sig, float bp_sigma,
                             float star_in_out, int32_t radius, const float *median_diff_stddev, nl_star *out, int32_t cap,
                             int32_t *counts, float *sum_of_shifts, float *avg_hfr, double *seconds_device, double *seconds_host) {
     NL_REQUIRE(ctx && counts && sum_of_shifts && avg_hfr && location && scale && host_frames, "NULL argument");
     NL_REQUIRE(n_frames >= 0 && len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(n_frames <= 65535, "more than 65535 frames in one batch");
     NL_REQUIRE(bp_sigma <= 0 || median_diff_stddev, "median_diff_stddev is needed when bp_sigma > 0");
+    for (int i = 0; i < n_frames; i++) { counts[i] = 0; sum_of_shifts[i] = 0.0f; avg_hfr[i] = 0.0f; }
+    if (seconds_device) *seconds_device = 0.0;
+    if (seconds_host) *seconds_host = 0.0;
+    if (n_frames == 0 || len == 0) return NL_OK;
+    NL_REQUIRE(dev_frames, "data is NULL");
+    NL_GUARD(ctx);
     std::vector<float> thr((size_t)n_frames);
     for (int i = 0; i < n_frames; i++) thr[i] = location[i] + scale[i] * star_sig;            // findstars.go:61
-    // every candidate is needed (the filters follow): size the per-frame list generously, redo if a frame has more
-    int scan_cap = cap > 65536 ? cap : 65536;
-    std::vector<nl_star> cand;
     std::vector<int32_t> n_cand((size_t)n_frames);
     const auto t0 = std::chrono::steady_clock::now();
-    for (;;) {
-        cand.resize((size_t)n_frames * scan_cap);
-        int rc = nl_find_bright_batch_dev(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, cand.data(), scan_cap,
-                                          n_cand.data());
-        if (rc != NL_OK) return rc;
-        int most = 0;
-        for (int i = 0; i < n_frames; i++) most = n_cand[i] > most ? n_cand[i] : most;
-        if (most <= scan_cap) break;
-        scan_cap = most;
-    }
+    nl_star *list = nullptr;
+    long long stride = 0;
+    int rc = bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, 0x7fffffff, &list, &stride,
+                               n_cand.data());                         // every candidate is needed: the filters follow
+    if (rc != NL_OK) return rc;
     const auto t1 = std::chrono::steady_clock::now();
     unsigned hw = std::thread::hardware_concurrency();
     const int n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, (unsigned)n_frames));
@@ -700,7 +733,7 @@ int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fram
     for (int t = 0; t < n_threads; t++)
         th.emplace_back([&]() {
             for (int i = next++; i < n_frames; i = next++)
-                counts[i] = find_stars_sparse(cand.data() + (size_t)i * scan_cap, n_cand[i], host_frames[i], len, width, location[i], scale[i],
+                counts[i] = find_stars_sparse(list + (size_t)i * stride, n_cand[i], host_frames[i], len, width, location[i], scale[i],
                                               star_sig, bp_sigma, star_in_out, radius, median_diff_stddev ? median_diff_stddev[i] : 0.0f,
                                               out + (size_t)i * cap, cap, sum_of_shifts + i, avg_hfr + i);
         });
