@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -232,6 +233,122 @@ __global__ void __launch_bounds__(256) bright_compact_kernel(const nl_star *__re
         const long long dst = (long long)row_offset[fr] + lane;
         if (dst < list_stride) list[(long long)blockIdx.y * list_stride + dst] = slots[fr * BRIGHT_SLOTS + lane];
     }
+}
+
+// ---- the two window passes of FindStars on the device, one thread per star, all frames of a batch in one launch -------
+// shiftToCenterOfMass (findstars.go:274-322): up to ten rounds of first moments over the (2r+1)^2 window around the
+// star, summed in raster order in fp32 exactly like the reference (a thread walks its window sequentially; the
+// windows of neighbouring stars overlap in L1/L2).  calcAndFilterHalfFluxRadius (findstars.go:327-396): the half-flux
+// radius over the disc and the inner / outer mass test.  Both update the star records in place (mapped pinned host
+// memory: a few megabytes for a whole batch) and leave the order-dependent parts -- the sums of the shifts and of the
+// radii, the compaction of the survivors -- to the host.
+// int32(float) as Go on amd64 (and the C oracle) computes it: CVTTSS2SI yields 0x80000000 for NaN and out-of-range
+// values, where the GPU's conversion saturates
+__device__ __forceinline__ int go_int32(float v) {
+    return (v >= -2147483648.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(128) star_com_kernel(const float *__restrict__ frames, long long frame_stride, int len, int width,
+                                                       const float *__restrict__ thresholds, int radius, nl_star *__restrict__ lists,
+                                                       long long list_stride, const int *__restrict__ counts, float *__restrict__ shifts) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[frame]) return;
+    const float *data = frames + (long long)frame * frame_stride;
+    const float threshold = thresholds[frame];
+    nl_star s = lists[(long long)frame * list_stride + i];
+    float shift_sq = 3.40282346638528859811704183484516925440e+38f;
+    for (int round = 0; shift_sq > 0.0001f && round < 10; round++) {
+        float xm = 0.0f, ym = 0.0f, mass = 0.0f;
+        for (int y = -radius; y <= radius; y++) {
+            const float fy = (float)y;
+            for (int x = -radius; x <= radius; x++) {
+                const int index = s.index + y * width + x;
+                float value = 0.0f;
+                if (index >= 0 && index < len) {
+                    value = __ldg(data + index) - threshold;
+                    if (value < 0) value = 0;
+                }
+                xm += (float)x * value;
+                ym += fy * value;
+                mass += value;
+            }
+        }
+        const int x = s.index % width, y = s.index / width;
+        if (mass == 0.0f) mass = 1e-8f;
+        const float dx = xm / mass, dy = ym / mass;
+        const float nx = (float)x + dx, ny = (float)y + dy;
+        const float pdx = nx - s.x, pdy = ny - s.y;
+        shift_sq = pdx * pdx + pdy * pdy;
+        const int index = (int)((unsigned)s.index + (unsigned)width * (unsigned)go_int32(dy + 0.5f) + (unsigned)go_int32(dx + 0.5f));   // (wraps like Go)
+        float value = 0.0f;
+        if (index >= 0 && index < len) value = __ldg(data + index);
+        s.index = index; s.value = value; s.x = nx; s.y = ny; s.mass = mass; s.hfr = 0.0f;
+    }
+    lists[(long long)frame * list_stride + i] = s;
+    shifts[(long long)frame * list_stride + i] = sqrtf(shift_sq);
+}
+
+__global__ void __launch_bounds__(128) star_hfr_kernel(const float *__restrict__ frames, long long frame_stride, int len, int width,
+                                                       const float *__restrict__ locations, float radius, float star_in_out,
+                                                       nl_star *__restrict__ lists, long long list_stride, const int *__restrict__ counts,
+                                                       unsigned char *__restrict__ keep) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[frame]) return;
+    const float *data = frames + (long long)frame * frame_stride;
+    const float location = locations[frame];
+    nl_star s = lists[(long long)frame * list_stride + i];
+    float moment = 0.0f, mass = 0.0f;
+    int pixels = 0;
+    const int rad = (int)ceil((double)radius);
+    int lim = (int)ceil((double)(radius + 1e-8f) * (double)(radius + 1e-8f));
+    for (int y = -rad; y <= rad; y++)
+        for (int x = -rad; x <= rad; x++) {
+            const int dsq = x * x + y * y;
+            if (dsq > lim) continue;
+            const float distance = (float)sqrt((double)dsq);
+            const int index = s.index + y * width + x;
+            float value = 0.0f;
+            if (index >= 0 && index < len) {
+                const float v = __ldg(data + index) - location;
+                if (v > 0) value = v;
+            }
+            moment += distance * value;
+            mass += value;
+            pixels++;
+        }
+    if (mass == 0.0f) mass = 1e-8f;
+    const float hfr = moment / mass;
+    bool ok = !(hfr > radius);
+    if (ok) {
+        float inner_mass = 0.0f;
+        int inner_pixels = 0;
+        const int irad = (int)ceil((double)hfr);
+        lim = (int)ceil((double)(hfr * hfr));
+        for (int y = -irad; y <= irad; y++)
+            for (int x = -irad; x <= irad; x++) {
+                const int dsq = x * x + y * y;
+                if (dsq > lim) continue;
+                const int index = s.index + y * width + x;
+                float value = 0.0f;
+                if (index >= 0 && index < len) {
+                    const float v = __ldg(data + index) - location;
+                    if (v > 0) value = v;
+                }
+                inner_mass += value;
+                inner_pixels++;
+            }
+        const float outer_mass = mass - inner_mass;
+        const int outer_pixels = pixels - inner_pixels;
+        if (inner_mass * (float)outer_pixels <= star_in_out * outer_mass * (float)inner_pixels) ok = false;
+    }
+    if (ok) {
+        s.hfr = hfr;
+        s.mass = mass;
+        lists[(long long)frame * list_stride + i] = s;
+    }
+    keep[(long long)frame * list_stride + i] = ok ? 1 : 0;
 }
 
 int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total) {
@@ -698,16 +815,18 @@ int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fra
     return NL_OK;
 }
 
-// FindStars over all frames of a resident stack: one batched scan on the device, then the sparse per-star steps of
-// every frame on host threads (they read the host copies of the frames, host_frames[i]) working in place on the
-// candidate lists the scan left in pinned host memory.  Per-frame inputs and outputs are arrays of n_frames entries;
-// out receives frame i's stars at out + i*cap.
+// FindStars over all frames of a resident stack.  Device: the batched scan, the centre-of-mass iterations and the
+// half-flux radius (one thread per star, all frames per launch).  Host threads (one frame each): the order-dependent
+// sparse steps between them -- bad-pixel rejection, the unstable quicksort by mass, the greedy overlap filter, the
+// sequential sums -- working in place on the candidate lists in mapped pinned memory; host_frames[i] are the host
+// copies of the frames (the bad-pixel rejection gathers from them).  Per-frame inputs and outputs are arrays of n_frames
+// entries; out receives frame i's stars at out + i*cap.
 int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, const float *const *host_frames,
                             int32_t len, int32_t width, const float *location, const float *scale, float star_sig, float bp_sigma,
                             float star_in_out, int32_t radius, const float *median_diff_stddev, nl_star *out, int32_t cap,
                             int32_t *counts, float *sum_of_shifts, float *avg_hfr, double *seconds_device, double *seconds_host) {
     NL_REQUIRE(ctx && counts && sum_of_shifts && avg_hfr && location && scale && host_frames, "NULL argument");
-    NL_REQUIRE(n_frames >= 0 && len >= 0 && width > 0 && cap >= 0, "bad size");
+    NL_REQUIRE(n_frames >= 0 && len >= 0 && width > 0 && cap >= 0 && radius >= 0, "bad size");
     NL_REQUIRE(n_frames <= 65535, "more than 65535 frames in one batch");
     NL_REQUIRE(bp_sigma <= 0 || median_diff_stddev, "median_diff_stddev is needed when bp_sigma > 0");
     for (int i = 0; i < n_frames; i++) { counts[i] = 0; sum_of_shifts[i] = 0.0f; avg_hfr[i] = 0.0f; }
@@ -716,31 +835,117 @@ int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fram
     if (n_frames == 0 || len == 0) return NL_OK;
     NL_REQUIRE(dev_frames, "data is NULL");
     NL_GUARD(ctx);
-    std::vector<float> thr((size_t)n_frames);
-    for (int i = 0; i < n_frames; i++) thr[i] = location[i] + scale[i] * star_sig;            // findstars.go:61
-    std::vector<int32_t> n_cand((size_t)n_frames);
-    const auto t0 = std::chrono::steady_clock::now();
-    nl_star *list = nullptr;
-    long long stride = 0;
-    int rc = bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, 0x7fffffff, &list, &stride,
-                               n_cand.data());                         // every candidate is needed: the filters follow
-    if (rc != NL_OK) return rc;
-    const auto t1 = std::chrono::steady_clock::now();
+    typedef std::chrono::steady_clock clk;
+    double t_dev = 0.0, t_host = 0.0;
+    auto since = [](clk::time_point t) { return std::chrono::duration<double>(clk::now() - t).count(); };
     unsigned hw = std::thread::hardware_concurrency();
     const int n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, (unsigned)n_frames));
-    std::atomic<int> next{0};
-    std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; t++)
-        th.emplace_back([&]() {
-            for (int i = next++; i < n_frames; i = next++)
-                counts[i] = find_stars_sparse(list + (size_t)i * stride, n_cand[i], host_frames[i], len, width, location[i], scale[i],
-                                              star_sig, bp_sigma, star_in_out, radius, median_diff_stddev ? median_diff_stddev[i] : 0.0f,
-                                              out + (size_t)i * cap, cap, sum_of_shifts + i, avg_hfr + i);
-        });
-    for (auto &t : th) t.join();
-    const auto t2 = std::chrono::steady_clock::now();
-    if (seconds_device) *seconds_device = std::chrono::duration<double>(t1 - t0).count();
-    if (seconds_host) *seconds_host = std::chrono::duration<double>(t2 - t1).count();
+    auto each_frame = [&](const std::function<void(int)> &f) {
+        std::atomic<int> next{0};
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&]() { for (int i = next++; i < n_frames; i = next++) f(i); });
+        for (auto &t : th) t.join();
+    };
+
+    // ---- device: the scan.  Every candidate is needed: the filters follow.
+    auto t0 = clk::now();
+    std::vector<float> thr((size_t)n_frames);
+    for (int i = 0; i < n_frames; i++) thr[i] = location[i] + scale[i] * star_sig;            // findstars.go:61
+    std::vector<int32_t> m((size_t)n_frames);
+    nl_star *list = nullptr;
+    long long stride = 0;
+    int rc = bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, 0x7fffffff, &list, &stride, m.data());
+    if (rc != NL_OK) return rc;
+    nl_star *dev_list = (nl_star *)((char *)ctx->batch_pinned_dev + ((char *)list - (char *)ctx->batch_pinned));
+    t_dev += since(t0);
+
+    // ---- host: rejectBadPixels, QSortStarsDesc, filterOutOverlaps (findstars.go:66-74)
+    t0 = clk::now();
+    each_frame([&](int i) {
+        nl_star *st = list + (size_t)i * stride;
+        int k = m[i];
+        if (bp_sigma > 0) k = reject_bad_pixels(st, k, host_frames[i], len, width, bp_sigma, median_diff_stddev[i]);
+        qsort_stars_desc(st, k);
+        m[i] = filter_out_overlaps(st, k, width, len / width, radius);
+    });
+    t_host += since(t0);
+
+    // ---- device: shiftToCenterOfMass.  Per-frame scalars and per-star outputs in a second pinned block.
+    t0 = clk::now();
+    const size_t per_frame = ((sizeof(int) + 2 * sizeof(float)) * (size_t)n_frames + 255) & ~(size_t)255;
+    const size_t aux_bytes = per_frame + (sizeof(float) + 1) * (size_t)n_frames * (size_t)stride + 256;
+    rc = ensure_pinned(ctx, aux_bytes);
+    if (rc != NL_OK) return rc;
+    int *h_counts = (int *)ctx->pinned;
+    float *h_thr2 = (float *)(h_counts + n_frames), *h_loc = h_thr2 + n_frames;
+    float *h_shift = (float *)((char *)ctx->pinned + per_frame);
+    unsigned char *h_keep = (unsigned char *)(h_shift + (size_t)n_frames * stride);
+    char *d_aux = (char *)ctx->pinned_dev;
+    int max_m = 1;
+    for (int i = 0; i < n_frames; i++) {
+        h_counts[i] = m[i];
+        h_thr2[i] = location[i] + scale[i] * star_sig * 0.5f;                                   // findstars.go:77
+        h_loc[i] = location[i];
+        if (m[i] > max_m) max_m = m[i];
+    }
+    {
+        dim3 grid((unsigned)((max_m + 127) / 128), (unsigned)n_frames);
+        star_com_kernel<<<grid, 128, 0, ctx->stream>>>(dev_frames, frame_stride, len, width, (const float *)(d_aux + ((char *)h_thr2 - (char *)ctx->pinned)),
+                                                       radius, dev_list, stride, (const int *)d_aux,
+                                                       (float *)(d_aux + ((char *)h_shift - (char *)ctx->pinned)));
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    t_dev += since(t0);
+
+    // ---- host: the sum of the shifts in star order, then sort and overlap filter again (findstars.go:78-84)
+    t0 = clk::now();
+    each_frame([&](int i) {
+        nl_star *st = list + (size_t)i * stride;
+        float sos = 0.0f;
+        for (int k = 0; k < m[i]; k++) sos += h_shift[(size_t)i * stride + k];
+        sum_of_shifts[i] = sos;
+        qsort_stars_desc(st, m[i]);
+        m[i] = filter_out_overlaps(st, m[i], width, len / width, radius);
+    });
+    t_host += since(t0);
+
+    // ---- device: calcAndFilterHalfFluxRadius
+    t0 = clk::now();
+    max_m = 1;
+    for (int i = 0; i < n_frames; i++) { h_counts[i] = m[i]; if (m[i] > max_m) max_m = m[i]; }
+    {
+        dim3 grid((unsigned)((max_m + 127) / 128), (unsigned)n_frames);
+        star_hfr_kernel<<<grid, 128, 0, ctx->stream>>>(dev_frames, frame_stride, len, width, (const float *)(d_aux + ((char *)h_loc - (char *)ctx->pinned)),
+                                                       (float)radius, star_in_out, dev_list, stride, (const int *)d_aux,
+                                                       (unsigned char *)(d_aux + ((char *)h_keep - (char *)ctx->pinned)));
+        NL_CUDA(cudaGetLastError());
+        ctx->launches++;
+        NL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    t_dev += since(t0);
+
+    // ---- host: the survivors in order, their average radius (findstars.go:384-395), the caller's array
+    t0 = clk::now();
+    each_frame([&](int i) {
+        nl_star *st = list + (size_t)i * stride;
+        int remaining = 0;
+        float avg = 0.0f;
+        for (int k = 0; k < m[i]; k++) {
+            if (!h_keep[(size_t)i * stride + k]) continue;
+            st[remaining++] = st[k];
+            avg += st[remaining - 1].hfr;
+        }
+        avg /= (float)remaining;
+        avg_hfr[i] = avg;
+        counts[i] = remaining;
+        for (int k = 0; k < remaining && k < cap; k++) out[(size_t)i * cap + k] = st[k];
+    });
+    t_host += since(t0);
+    if (seconds_device) *seconds_device = t_dev;
+    if (seconds_host) *seconds_host = t_host;
     return NL_OK;
 }
 
