@@ -472,30 +472,63 @@ NL_HD float weighted_mean(const float *g, const IDX *gw, const float *wtab, int 
 // `changed` nor the sums of squares below can see.
 NL_HD float clampmm(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
+// One-sided clamps: winsor_sigma runs right after the quick-select, when the buffer is partitioned around slot
+// km1 = cur >> 1 (the upper median): slots below hold values <= median, slots from km1 on values >= median.  All bounds
+// of all rounds satisfy L, lo <= median <= H, hi, so below km1 only the lower bound can act and from km1 on only the
+// upper one -- one FMNMX and one compare per sample instead of four and one.  `changed` (the samples the round moved:
+// previous copy < lo or > hi) becomes: sample < lo counted when the lower bound rose (L < lo), sample > hi when the
+// upper one fell.  kmin / kmax: warp-uniform ends of the two one-sided ranges; the slots between them do both sides.
 template <int S>
-NL_HD float winsor_sigma(const float *g, int cur, float median, float sd) {
+NL_HD float winsor_sigma(const float *g, int cur, float median, float sd, int km1) {
     float L = -INFINITY, H = INFINITY;
+    const int kmin = NL_WARP_MIN(cur > 0 ? km1 : 0x7fffffff), kmax = NL_WARP_MAX(cur > 0 ? km1 : 0);
+    int e0 = cur < kmin ? cur : kmin;                       // [0, e0): lower bound only
+    int e1 = cur < kmax ? cur : kmax;                       // [e0, e1): both;  [e1, cur): upper bound only
+    if (!(fabsf(median) < INFINITY)) { e0 = 0; e1 = cur; }  // a median that overflowed (or NaN) orders nothing: both sides everywhere
     for (;;) {
         const float lo = nl_subf(median, nl_mulf(1.5f, sd));
         const float hi = nl_addf(median, nl_mulf(1.5f, sd));
+        const bool rise = L < lo, fall = H > hi;            // which bound moves this round
+        const float Ln = clampmm(L, lo, hi), Hn = clampmm(H, lo, hi);
         int changed = 0;
-        // clamp and first sum of MeanStdDev fused: the sum runs over the clamped values in order
+        // clamp and first sum of MeanStdDev fused: the sum runs over the clamped values in index order
         float s = 0.0f;
+        int i = 0;
 #pragma unroll 8
-        for (int i = 0; i < cur; i++) {
-            const float old = clampmm(g[i * S], L, H);   // the copy as the previous rounds left it
-            const float v = clampmm(old, lo, hi);
-            changed += (v != old) ? 1 : 0;               // old < lo or old > hi
-            s = nl_addf(s, v);
+        for (; i < e0; i++) {
+            const float x = g[i * S];
+            changed += (rise & (x < lo)) ? 1 : 0;
+            s = nl_addf(s, fmaxf(x, Ln));
         }
-        L = clampmm(L, lo, hi);
-        H = clampmm(H, lo, hi);
+        for (; i < e1; i++) {
+            const float x = g[i * S];
+            changed += ((rise & (x < lo)) | (fall & (x > hi))) ? 1 : 0;
+            s = nl_addf(s, clampmm(x, Ln, Hn));
+        }
+#pragma unroll 8
+        for (; i < cur; i++) {
+            const float x = g[i * S];
+            changed += (fall & (x > hi)) ? 1 : 0;
+            s = nl_addf(s, fminf(x, Hn));
+        }
+        L = Ln;
+        H = Hn;
         const float fn = (float)cur;
         const float m = nl_divf(s, fn);
         float var = 0.0f;
+        i = 0;
 #pragma unroll 8
-        for (int i = 0; i < cur; i++) {
+        for (; i < e0; i++) {
+            const float d = nl_subf(fmaxf(g[i * S], L), m);
+            var = nl_addf(var, nl_mulf(d, d));
+        }
+        for (; i < e1; i++) {
             const float d = nl_subf(clampmm(g[i * S], L, H), m);
+            var = nl_addf(var, nl_mulf(d, d));
+        }
+#pragma unroll 8
+        for (; i < cur; i++) {
+            const float d = nl_subf(fminf(g[i * S], H), m);
             var = nl_addf(var, nl_mulf(d, d));
         }
         var = nl_divf(var, fn);
@@ -731,7 +764,7 @@ NL_HD float reduce_winsor(float *g, IDX *gw, const float *wtab, int &cur, float 
         const float median = qselect_median<S, (S < 32)>(g, m);
         float mean, sd;
         mean_stddev<S>(g, m, mean, sd);
-        if (m > 0) sd = winsor_sigma<S>(g, m, median, sd);
+        if (NL_ANY(m > 0)) { const float wsd = winsor_sigma<S>(g, m, median, sd, m >> 1); if (m > 0) sd = wsd; }
         const float lo = nl_subf(median, nl_mulf(sig_lo, sd));
         const float hi = nl_addf(median, nl_mulf(sig_hi, sd));
         const int left = clip_pass<S, W, IDX>(g, gw, m, lo, hi, ncl, nch, m >> 1, sig_lo >= 0.0f && sig_hi >= 0.0f);

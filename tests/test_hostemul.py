@@ -126,3 +126,27 @@ def test_fuzz_shapes_modes_signed_zeros(hostemul, seed):
         got = emul_stack(hostemul, frames, mode, sl, sh, w, ref)
         assert bits_equal(got[0], want[0]), (it, n, p, mode, weighted, sl, sh, first_mismatch(got[0], want[0]))
         assert got[1:] == want[1:], (it, mode, got[1:], want[1:])
+
+
+def test_infinities_and_huge_values_every_mode(hostemul):
+    """IEEE corner values (the GPU test's data): +-inf samples, denormals, magnitudes whose sums and squares overflow --
+    the winsorized clamps must not assume an ordered median there"""
+    rng = np.random.default_rng(21)
+    n, p = 40, 600
+    frames = (rng.standard_normal((n, p)) * 10 + 100).astype(np.float32)
+    frames[3, 0:50] = np.inf
+    frames[7, 25:80] = -np.inf
+    frames[:, 100:150] = (rng.standard_normal((n, 50)) * 1e-41).astype(np.float32)
+    frames[:, 150:200] = (rng.standard_normal((n, 50)) * 1e30).astype(np.float32)
+    frames[5, 200:220] = np.float32(3e38)
+    frames[:, 220:240] = -0.0
+    frames[::2, 230:240] = 0.0
+    frames[:, 240:260] = np.float32(3.2e38)           # lower + upper of the median overflow
+    frames[::3, 240:260] = np.float32(-3.2e38)
+    for mode, weighted in mode_cases():
+        w = weights_for(n) if weighted else None
+        for sl, sh in ((2.75, 2.75), (1.0, 0.5)):
+            a = O.stack(frames, mode, sl, sh, weights=w)
+            b = emul_stack(hostemul, frames, mode, sl, sh, w)
+            assert bits_equal(a[0], b[0]), (mode, weighted, sl, first_mismatch(a[0], b[0]))
+            assert a[1:] == b[1:], (mode, weighted)
