@@ -187,9 +187,23 @@ static void writeCard(std::string &sb, std::string key, const std::string &value
     sb += buf;
 }
 
+// Go's %g of a float32 (write.go:135-139 via fmt): the SHORTEST decimal that parses back to the same float32, in %e
+// form when the decimal exponent is < -4 or >= 6 (strconv.FormatFloat(v, 'g', -1, 32): eprec = 6 for shortest)
 static std::string gfloat(float v) {
     char b[64];
-    snprintf(b, sizeof b, "%g", (double)v);
+    if (v != v) return "NaN";
+    if (v == INFINITY) return "+Inf";
+    if (v == -INFINITY) return "-Inf";
+    int prec = 0;
+    for (; prec < 9; prec++) {                               // digits after the first: 0 .. 8 (9 significant digits always suffice)
+        snprintf(b, sizeof b, "%.*e", prec, (double)v);
+        if (strtof(b, nullptr) == v) break;
+    }
+    std::string e = b;                                       // d.ddddde[+-]XX
+    const size_t ep = e.find('e');
+    const int exp10 = atoi(e.c_str() + ep + 1);
+    if (exp10 < -4 || exp10 >= 6) return e;                  // Go prints at least two exponent digits, like C
+    snprintf(b, sizeof b, "%.*f", prec - exp10 > 0 ? prec - exp10 : 0, (double)v);
     return b;
 }
 

@@ -81,3 +81,20 @@ def test_header_errors(shim, tmp_path):
     out = np.empty(4, np.float32)
     assert shim.nlh_fits_read(p.encode(), out.ctypes.data_as(C.c_void_p), 4, out.ctypes.data_as(C.c_void_p)) == -1
     assert b"SIMPLE=T missing" in shim.nlh_last_error()
+
+
+def test_header_floats_are_the_shortest_round_trip_like_go(shim, tmp_path):
+    """write.go formats EXPOSURE / BZERO / BSCALE with Go's %g of a float32: the shortest decimal that parses back to
+    the same float32, exponent form from 1e6 up and below 1e-4 (C's %g would cut 12345.67 to 12345.7)"""
+    img = np.zeros((2, 3), np.float32)
+    nax = np.array([3, 2], np.int32)
+    for exposure, want in ((12345.67, "12345.67"), (300.0, "300"), (0.1, "0.1"), (1234567.0, "1.234567e+06"),
+                           (1e-5, "1e-05"), (2.5e10, "2.5e+10"), (16777216.0, "1.6777216e+07"), (0.33333334, "0.33333334")):
+        path = str(tmp_path / "e.fits")
+        rc = shim.nlh_fits_write(path.encode(), img.ctypes.data_as(C.c_void_p), nax.ctypes.data_as(C.c_void_p), 2, exposure)
+        assert rc == 0, shim.nlh_last_error()
+        head = open(path, "rb").read(2880).decode("ascii")
+        cards = {head[i:i + 8].strip(): head[i + 10:i + 30].strip() for i in range(0, 2880, 80)}
+        assert cards["EXPOSURE"] == want, (exposure, cards["EXPOSURE"])
+        assert np.float32(float(cards["EXPOSURE"])) == np.float32(exposure)
+        assert cards["BZERO"] == "0" and cards["BSCALE"] == "1"
