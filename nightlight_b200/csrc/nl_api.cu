@@ -186,6 +186,7 @@ int nl_ctx_set_tuning(nl_ctx *ctx, const char *key, const char *value) {
         return NL_OK;
     }
     if (k == "linfit_stream") { ctx->linfit_stream = atoi(v.c_str()); return NL_OK; }
+    if (k == "linfit_stream_cache") { ctx->linfit_stream_cache = atoi(v.c_str()); return NL_OK; }
     if (k == "linfit_stream_ctas") { ctx->linfit_stream_ctas = atoi(v.c_str()); return NL_OK; }
     if (k == "stats_debug") { ctx->stats_debug = atoi(v.c_str()) != 0; return NL_OK; }
     if (k == "stats_force_replay") { ctx->stats_force_replay = atoi(v.c_str()) != 0; return NL_OK; }

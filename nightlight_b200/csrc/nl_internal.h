@@ -47,6 +47,7 @@ struct nl_ctx {
     int defer_at[8] = {0};
     int tile_width = 0;              // "tile_width": 32 / 16 / 8 / 1 forces the tile width of the column kernel, 0 = automatic
     int linfit_stream = 1;           // "linfit_stream": 0 = long columns take the in-place linear-fit kernel instead of the streaming rounds
+    int linfit_stream_cache = -1;    // "linfit_stream_cache": at most this many cached blocks per column (-1 = what fits)
     int linfit_stream_ctas = 0;      // "linfit_stream_ctas": CTAs per SM of the streaming rounds kernel (0 = what fits)
     bool stats_debug = false;        // "stats_debug": the frame statistics print their interval proofs to stderr
     bool stats_force_replay = false; // "stats_force_replay": always replay the float64 chains in order

@@ -167,6 +167,7 @@ static int stack_launch(nl_stack_job *job, int mode, const float *host_weights, 
     a.ref_loc = ref_loc; a.sig_lo = sig_lo; a.sig_hi = sig_hi; a.out = dev_out; a.clip = job->clip; a.tile_counter = job->clip + 2;
     a.defer_passes = 0; a.phase = 0; a.pool_in = StackArgs::Pool{nullptr, nullptr, nullptr, nullptr, job->clip + 3, 0};
     a.pool_out = a.pool_in; a.pool_tile_counter = job->clip + 4;
+    a.stream_cache_blocks = 0;
     a.n_peers = n_peers;
     for (int e = 0; e < NL_MAX_PEERS; e++) a.peer_out[e] = e < n_peers ? peer_outs[e] : nullptr;
     switch (mode) {
@@ -386,7 +387,7 @@ static int stack_apply_range(nl_ctx *ctx, const float *const *host_frames, int32
                 lc->defer_override = ctx->defer_override; lc->defer_n = ctx->defer_n;
                 for (int i = 0; i < 8; i++) lc->defer_at[i] = ctx->defer_at[i];
                 lc->tile_width = ctx->tile_width;
-                lc->linfit_stream = ctx->linfit_stream; lc->linfit_stream_ctas = ctx->linfit_stream_ctas;
+                lc->linfit_stream = ctx->linfit_stream; lc->linfit_stream_ctas = ctx->linfit_stream_ctas; lc->linfit_stream_cache = ctx->linfit_stream_cache;
             }
         }
         if (rc == NL_OK && (lane_px > ctx->lane_px[l] || n_frames != ctx->lane_frames[l] || !ctx->lane_job[l])) {   // (re)size the lane

@@ -33,6 +33,7 @@ struct StackArgs {
     // finished -- their state is exactly the (permuted or sorted) survivors and their count -- into a pool in
     // global memory; the next launch runs the same kernel over that pool, 32 unfinished columns to a warp, and may
     // defer again into a second pool.  The arithmetic of a column is unchanged.
+    int stream_cache_blocks; // streaming linear fit: 32-sample blocks of every column kept in shared memory
     int defer_passes;        // 0: run every column to the end
     int phase;               // 0: tiles of the frame stack; >= 1: tiles of the input pool
     struct Pool {
@@ -502,30 +503,47 @@ struct BlockStream {
     }
 };
 
-// walks the blocks of the warp's columns: f(b, v) gets the 32 samples of block b of THIS lane's column.  A ring of
-// STREAM_DEPTH buffers: the copies of the next STREAM_DEPTH-1 blocks are in flight while the lanes work on one (with few
-// warps per SM -- the columns in flight must fit the L2 -- one block ahead does not cover the L2 latency).
+// walks the blocks of the warp's columns: f(b, v) gets the 32 samples of block b of THIS lane's column.  The first
+// `cb` blocks of every column stay in shared memory for the whole launch (FILL: this walk puts them there) -- the kernel
+// is bound by the bytes it moves, every cached block saves three reads per round; the others come through a ring of
+// STREAM_DEPTH buffers: the copies of the next STREAM_DEPTH-1 blocks are in flight while the lanes work on one, and the
+// ring is started before the cached blocks are worked on, so their arithmetic covers its first latency.
 #ifndef NL_STREAM_DEPTH
-#define NL_STREAM_DEPTH 4
+#define NL_STREAM_DEPTH 3
 #endif
 constexpr int STREAM_DEPTH = NL_STREAM_DEPTH;
-template <typename F>
-__device__ __forceinline__ void stream_blocks(const BlockStream &bs, const float *stage, int nblk, F &&f) {
+template <bool FILL, typename F>
+__device__ __forceinline__ void stream_blocks(const BlockStream &bs, float *stage, float *cache, int cb, int b0, int nblk, F &&f) {
+    // blocks [b0, nblk) of the columns (warp-uniform: blocks whose samples are rejected in every lane are not read)
     const int lane = threadIdx.x & 31;
+    const int first = FILL ? b0 : (cb < nblk ? (cb > b0 ? cb : b0) : nblk);          // blocks [first, nblk) are streamed
 #pragma unroll
     for (int d = 0; d < STREAM_DEPTH - 1; d++) {
-        if (d < nblk) bs.issue(d, d); else cp_async_commit();
+        if (first + d < nblk) bs.issue(first + d, d); else cp_async_commit();
     }
 #pragma unroll 1
-    for (int b = 0; b < nblk; b++) {
-        const int ahead = b + STREAM_DEPTH - 1;
-        if (ahead < nblk) bs.issue(ahead, ahead % STREAM_DEPTH); else cp_async_commit();     // (an empty group keeps the count)
-        cp_async_wait<STREAM_DEPTH - 1>();
-        __syncwarp();
-        const float *src = stage + (b % STREAM_DEPTH) * 1024 + lane;
+    for (int b = b0; b < first; b++) {
+        const float *src = cache + b * 1024 + lane;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = src[j * 32];
+        f(b, v);
+    }
+#pragma unroll 1
+    for (int b = first; b < nblk; b++) {
+        const int rel = b - first, ahead = b + STREAM_DEPTH - 1;
+        if (ahead < nblk) bs.issue(ahead, (rel + STREAM_DEPTH - 1) % STREAM_DEPTH); else cp_async_commit();     // (an empty group keeps the count)
+        cp_async_wait<STREAM_DEPTH - 1>();
+        __syncwarp();
+        const float *src = stage + (rel % STREAM_DEPTH) * 1024 + lane;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = src[j * 32];
+        if (FILL && b < cb) {
+            float *dst = cache + b * 1024 + lane;
+#pragma unroll
+            for (int j = 0; j < 32; j++) dst[j * 32] = v[j];
+        }
         f(b, v);
         __syncwarp();                                               // the buffer is refilled STREAM_DEPTH-1 blocks later
     }
@@ -535,13 +553,15 @@ __device__ __forceinline__ void stream_blocks(const BlockStream &bs, const float
 template <int S>
 __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel(StackArgs a) {
     static_assert(S == 8, "the streaming rounds read pools of 8-pixel tiles");
-    extern __shared__ __align__(128) unsigned char stream_smem[];      // per warp: STREAM_DEPTH 4 KiB block buffers, then the survivor masks [word][lane]
+    extern __shared__ __align__(128) unsigned char stream_smem[];      // per warp: STREAM_DEPTH 4 KiB ring buffers, the cached blocks, the survivor masks [word][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npad = (a.n + 31) & ~31;
     const int nwords = npad >> 5;
-    const size_t per_warp = 4096 * STREAM_DEPTH + (size_t)nwords * 128;
+    const int cb = a.stream_cache_blocks;
+    const size_t per_warp = 4096 * (size_t)(STREAM_DEPTH + cb) + (size_t)nwords * 128;
     float *stage = reinterpret_cast<float *>(stream_smem + (size_t)warp * per_warp);
-    unsigned *alive = reinterpret_cast<unsigned *>(stream_smem + (size_t)warp * per_warp + 4096 * STREAM_DEPTH) + lane;   // word w at alive[w * 32]
+    float *cache = stage + 1024 * STREAM_DEPTH;
+    unsigned *alive = reinterpret_cast<unsigned *>(stream_smem + (size_t)warp * per_warp + 4096 * (size_t)(STREAM_DEPTH + cb)) + lane;   // word w at alive[w * 32]
     const unsigned long long cnt = *a.pool_in.count;
     const long long pool_slots = cnt < (unsigned long long)a.pool_in.cap ? (long long)cnt : a.pool_in.cap;
     const long long groups = (pool_slots + 31) / 32;
@@ -563,7 +583,7 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
         const int nblk = (__reduce_max_sync(0xffffffffu, cur) + 31) >> 5;
         // the survivors' masks, and the sum of the samples in index order (first chain of MeanStdDev, stats.go:247-250)
         float ysum = 0.0f;
-        stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+        stream_blocks<true>(bs, stage, cache, cb, 0, nblk, [&](int b, const float (&v)[32]) {
             const int rem = cur - b * 32;
             const unsigned w = rem >= 32 ? 0xffffffffu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
             alive[b * 32] = w;
@@ -576,6 +596,7 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
         bool mine = true, spilled = false;
         float res = 0.0f;
         int limit = a.defer_passes;
+        int blo = 0, bhi = nblk;                                       // blocks that still hold a survivor in some lane
         for (;;) {
             int round = 0;
             while (__any_sync(0xffffffffu, !done)) {
@@ -592,7 +613,7 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
                 const float fm = (float)m;
                 const float ym = nl_divf(ysum, fm);
                 float yvar = 0.0f, corr = 0.0f, fi = 0.0f;
-                stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                stream_blocks<false>(bs, stage, cache, cb, blo, bhi, [&](int b, const float (&v)[32]) {
                     const unsigned w = done ? 0u : alive[b * 32];
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
@@ -611,7 +632,7 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
                 // mean absolute residual, stack.go:878-886
                 float sigma = 0.0f;
                 fi = 0.0f;
-                stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                stream_blocks<false>(bs, stage, cache, cb, blo, bhi, [&](int b, const float (&v)[32]) {
                     const unsigned w = done ? 0u : alive[b * 32];
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
@@ -628,8 +649,9 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
                 const float lob = nl_mulf(a.sig_lo, sigma), hib = nl_mulf(a.sig_hi, sigma);
                 float nsum = 0.0f;
                 int left = 0;
+                int first_b = 0x7fffffff, last_b = -1;                 // this lane's first and last block with a survivor
                 fi = 0.0f;
-                stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+                stream_blocks<false>(bs, stage, cache, cb, blo, bhi, [&](int b, const float (&v)[32]) {
                     const unsigned w = done ? 0u : alive[b * 32];
                     // (the tests of dead samples set garbage bits, masked below; x only advances over survivors)
                     unsigned lowm = 0u, highm = 0u;
@@ -647,7 +669,12 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
                     const unsigned keep = w & ~(lowm | highm);
                     if (keep != w) alive[b * 32] = keep;
                     left += __popc(keep);
+                    if (keep != 0u) { first_b = first_b < b ? first_b : b; last_b = b; }
                 });
+                {
+                    const int nlo = __reduce_min_sync(0xffffffffu, first_b), nhi = __reduce_max_sync(0xffffffffu, last_b) + 1;
+                    if (nlo < nhi) { blo = nlo; bhi = nhi; }           // (no survivor anywhere: every lane is done after this round)
+                }
                 if (!done) {
                     mean = ym;
                     if (left == cur || cur < 3) done = true;          // nothing rejected || len < 3
@@ -668,7 +695,7 @@ __global__ void __launch_bounds__(LINFIT_STREAM_WARPS * 32) linfit_rounds_kernel
             const long long wslot = spilled ? oslot : 0;
             float *dst = a.pool_out.samples + (wslot / S) * ((long long)npad * S) + (wslot % S);
             int wpos = 0;
-            stream_blocks(bs, stage, nblk, [&](int b, const float (&v)[32]) {
+            stream_blocks<false>(bs, stage, cache, cb, blo, bhi, [&](int b, const float (&v)[32]) {
                 const unsigned w = spilled ? alive[b * 32] : 0u;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
@@ -842,12 +869,23 @@ inline int launch_linfit_stream(nl_stack_job *job, const StackArgs &args, bool *
     DeferSchedule d = defer_schedule(ST_LINFIT, ctx);
     if (ctx->defer_override && d.n == 0) return NL_OK;                 // "0": the single-launch kernel was asked for
     const int nwords = ((job->n + 31) & ~31) >> 5;
-    const size_t smem = (size_t)LINFIT_STREAM_WARPS * (4096 * STREAM_DEPTH + (size_t)nwords * 32 * sizeof(unsigned));
-    if (smem > (size_t)ctx->max_smem_optin) return NL_OK;
+    // shared memory per warp: the ring, the survivor masks, and as many cached blocks of the columns as one CTA per SM holds
+    const size_t fixed = 4096 * (size_t)STREAM_DEPTH + (size_t)nwords * 32 * sizeof(unsigned);
+    if ((size_t)LINFIT_STREAM_WARPS * fixed > (size_t)ctx->max_smem_optin) return NL_OK;
+    int cache_blocks = (int)(((size_t)ctx->max_smem_optin / LINFIT_STREAM_WARPS - fixed) / 4096);
+    if (cache_blocks > nwords) cache_blocks = nwords;
+    if (ctx->linfit_stream_cache >= 0 && cache_blocks > ctx->linfit_stream_cache) cache_blocks = ctx->linfit_stream_cache;
+    const size_t smem = (size_t)LINFIT_STREAM_WARPS * (fixed + 4096 * (size_t)cache_blocks);
     const double frac[2] = {1.0, 0.85};
     StackArgs::Pool pools[2];
     if (!ensure_pools(job, 0, frac, pools) || pools[0].cap < ((job->pixels + 31) & ~31ll)) return NL_OK;
     if (pools[1].cap < 32) d.n = 0;                                    // no second pool: sort, then one launch to the end
+    if (!ctx->defer_override) {
+        // every regrouping launch ends in a tail of half-idle SMs: small jobs regroup once or not at all
+        const long long groups = (job->pixels + 31) / 32, lanes = (long long)ctx->sm_count * LINFIT_STREAM_WARPS;
+        if (groups < 2 * lanes) d.n = 0;
+        else if (groups < 8 * lanes) { d.n = 1; d.at[0] = 12; }
+    }
     auto kern = linfit_rounds_kernel<S>;
     NL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
@@ -857,6 +895,7 @@ inline int launch_linfit_stream(nl_stack_job *job, const StackArgs &args, bool *
     const unsigned grid = (unsigned)(ctx->sm_count * ctas_per_sm);
     StackArgs a2 = args;
     a2.phase = 0;
+    a2.stream_cache_blocks = cache_blocks;
     a2.pool_out = pools[0];
     a2.pool_out.count = job->clip + 3;
     {
