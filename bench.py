@@ -19,8 +19,8 @@ is fused into the stack kernel's epilogue (peer stores over NVLink) or, with --g
 Other configurations (BASELINE.json configs[1..4]), same JSON contract:
   c2w  256 x 4096^2, winsorized sigma clip + inverse-noise weights (noise estimated on the device)
   c4   1024 x 8192^2, linear-fit stacking, 1024-row stripes per GPU (8 GPUs = the whole image)
-  c5   4096 x 4096^2, batches sized from the device memory (OpStackBatches.partition), sigma goal-seek on the first
-       batch (count-only trial stacks), stack of stacks per stripe, one reassembly at the end
+  c5   4096 x 4096^2, batches sized by OpStackBatches.partition from the device memory (capped at 256 frames per batch),
+       sigma goal-seek on the first batch (count-only trial stacks), stack of stacks per stripe, one reassembly
   c3   star detection + resample + stack over 64 x 6000x4000 resident frames (one GPU)
 
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads, the reference's own 8 MiB
@@ -657,7 +657,11 @@ def run_c5(args, cfg):
     free_b, total_b = ctx.mem_info()
     # OpStackBatches.partition (stackbatches.go:121-210) with the device's free memory in the place of StackMemoryMB:
     # 60 % of it for the frames of a batch (the rest: the pool of deferred columns, accumulator, result)
-    mem_mb = args.stack_memory_mb or int(free_b * 0.6) >> 20
+    # ... capped so that a batch holds at most 256 frames per column: beyond that the exact emulation of the reference's
+    # quick-select runs on narrower tiles and the stack slows down by an order of magnitude;
+    # --stack-memory-mb sets the budget explicitly (e.g. the whole free memory: one batch of 4096 frames on 8 GPUs)
+    frame_mb = 4.0 * pixels / 2**20
+    mem_mb = args.stack_memory_mb or min(int(free_b * 0.6) >> 20, int((256 + 3) * frame_mb) + 1)
     if world > 1:                                       # every rank must cut the same batches
         t = torch.tensor([mem_mb], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -925,7 +929,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="multi-GPU reassembly of the stacked image")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--stack-memory-mb", type=int, default=0, help="c5: memory budget of a batch per GPU (default: 60 %% of the free device memory)")
+    ap.add_argument("--stack-memory-mb", type=int, default=0, help="c5: memory budget of a batch per GPU (default: 60 %% of the free device memory, capped at 256-frame batches)")
     ap.add_argument("--clip-perc-low", type=float, default=2.0, help="c5: target percentage of samples clipped on the low side")
     ap.add_argument("--clip-perc-high", type=float, default=2.0)
     ap.add_argument("--tune", default="", help="k=v,k=v: nl_ctx_set_tuning knobs of the library (A/B measurements; lists with ':')")
