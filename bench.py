@@ -716,6 +716,12 @@ def run_c5(args, cfg):
     # ---- pass 2: every batch stacked with the sigmas found, stack of stacks on the device, one reassembly
     gathered = torch.empty(pixels * world, dtype=torch.float32, device="cuda") if world > 1 else None
     acc_t = None
+    if world > 1:
+        # NCCL builds its all-gather channels on first use (>100 ms): outside the timed segments
+        acc_t = torch.zeros(pixels, dtype=torch.float32, device="cuda")
+        with torch.cuda.stream(env.ext):
+            dist.all_gather_into_tensor(gathered, acc_t)
+        env.barrier()
     stack_ms, k_ms_batches = 0.0, []
     clip_tot = [0, 0]
     steps = max(1, args.steps if args.steps_given else 1)
