@@ -58,6 +58,7 @@ namespace nl {
 int set_error(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int ensure_scratch(nl_ctx *ctx, size_t bytes);
+int lane_context(nl_ctx *ctx, int l, nl_ctx **out);                    // nl_stack.cu: ctx->lane_ctx[l], created on first use
 int ensure_frame(nl_ctx *ctx, int slot, size_t bytes, float **out);     // nl_api.cu
 int ensure_pinned(nl_ctx *ctx, size_t bytes);                           // nl_api.cu: ctx->pinned (mapped), at least `bytes`
 int exclusive_scan_launch(nl_ctx *ctx, const int *dev_counts, int *dev_offsets, int n, int *dev_total);   // nl_stars.cu

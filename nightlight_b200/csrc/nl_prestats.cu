@@ -23,6 +23,9 @@
 // Algorithmic bytes: median filter 8 B/pixel (4 read, 4 written); stats 4 B/pixel per pass (two passes:
 // the variance needs the rounded mean); bad-pixel scan 4 B/pixel per pass (count, write).
 #include "nl_internal.h"
+#include <thread>
+#include <atomic>
+#include <string>
 
 #include <float.h>
 #include <math.h>
@@ -788,14 +791,44 @@ int nl_bad_pixel_map_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_f
     NL_REQUIRE(dev_frames || n_frames == 0, "NULL frames");
     NL_REQUIRE(frame_stride % 4 == 0 && ((uintptr_t)dev_frames & 15) == 0, "frames must start on 16 bytes");
     NL_GUARD(ctx);
-    float *tmp = nullptr;
-    int rc = ensure_frame(ctx, 1, sizeof(float) * (size_t)len, &tmp);
-    if (rc != NL_OK) return rc;
-    for (int i = 0; i < n_frames; i++) {
-        rc = nl_bad_pixel_map_dev(ctx, dev_frames + (size_t)i * frame_stride, len, width, sigma_low, sigma_high, tmp,
-                                  host_bpm ? host_bpm + (size_t)i * cap : nullptr, host_bpm ? cap : 0, counts + i, stats + 4 * i);
+    // three frames in flight: the context and its two lanes (own stream, scratch and pinned read-back buffers each),
+    // one host thread per lane -- a frame's chain is a handful of short kernels and two host round trips, which the
+    // other two lanes fill
+    constexpr int WORKERS = 3;
+    nl_ctx *wc[WORKERS] = {ctx, nullptr, nullptr};
+    const int workers = n_frames < WORKERS ? (n_frames < 1 ? 1 : n_frames) : WORKERS;
+    for (int w = 1; w < workers; w++) {
+        int rc = lane_context(ctx, w - 1, &wc[w]);
         if (rc != NL_OK) return rc;
     }
+    NL_CUDA(cudaStreamSynchronize(ctx->stream));          // the frames were produced on the context's stream
+    std::atomic<int> next{0};
+    int64_t replays_of_lanes[WORKERS] = {0, 0, 0};
+    int rcs[WORKERS] = {NL_OK, NL_OK, NL_OK};
+    std::string msgs[WORKERS];
+    auto work = [&](int w) {
+        nl_ctx *c = wc[w];
+        CtxGuard g(c);
+        float *tmp = nullptr;
+        int rc = g.ok ? ensure_frame(c, 1, sizeof(float) * (size_t)len, &tmp) : set_error(NL_E_CUDA, "cudaSetDevice(%d) failed", c->device);
+        const int64_t launches0 = c->launches.load(), replays0 = c->exact_replays;
+        for (int i = next++; rc == NL_OK && i < n_frames; i = next++)
+            rc = nl_bad_pixel_map_dev(c, dev_frames + (size_t)i * frame_stride, len, width, sigma_low, sigma_high, tmp,
+                                      host_bpm ? host_bpm + (size_t)i * cap : nullptr, host_bpm ? cap : 0, counts + i, stats + 4 * i);
+        if (rc != NL_OK) msgs[w] = nl_last_error();       // (the message is per thread)
+        if (w > 0) {                                       // the lanes' work counts as the context's
+            ctx->launches += c->launches.load() - launches0;
+            replays_of_lanes[w] = c->exact_replays - replays0;
+        }
+        rcs[w] = rc;
+    };
+    std::thread th[WORKERS];
+    for (int w = 1; w < workers; w++) th[w] = std::thread(work, w);
+    work(0);
+    for (int w = 1; w < workers; w++) th[w].join();
+    for (int w = 1; w < workers; w++) ctx->exact_replays += replays_of_lanes[w];
+    for (int w = 0; w < workers; w++)
+        if (rcs[w] != NL_OK) return w == 0 ? rcs[w] : set_error(rcs[w], "%s", msgs[w].c_str());
     return NL_OK;
 }
 

@@ -349,6 +349,24 @@ int nl_stack_run(nl_stack_job *job, int32_t mode, const float *weights, float si
 
 namespace nl {
 
+// ctx->lane_ctx[l]: a second / third stream with its own scratch on the context's device, created on first use and kept
+// (nl_stack_apply's stripe lanes, the batched bad-pixel maps).  A lane inherits the settings of its context.
+int lane_context(nl_ctx *ctx, int l, nl_ctx **out) {
+    if (!ctx->lane_ctx[l]) {
+        int rc = nl_ctx_create(ctx->device, &ctx->lane_ctx[l]);
+        if (rc != NL_OK) return rc;
+    }
+    nl_ctx *lc = ctx->lane_ctx[l];
+    lc->defer_override = ctx->defer_override; lc->defer_n = ctx->defer_n;
+    for (int i = 0; i < 8; i++) lc->defer_at[i] = ctx->defer_at[i];
+    lc->tile_width = ctx->tile_width;
+    lc->linfit_stream = ctx->linfit_stream; lc->linfit_stream_ctas = ctx->linfit_stream_ctas; lc->linfit_stream_cache = ctx->linfit_stream_cache;
+    lc->numerics = ctx->numerics;
+    lc->stats_debug = ctx->stats_debug; lc->stats_force_replay = ctx->stats_force_replay;
+    *out = lc;
+    return NL_OK;
+}
+
 // The pixel range [p_begin, p_end) of an image stacked from host frames through one context: the range is cut into
 // n_stripes row stripes that alternate on the context's two lanes (a lane = stream + job + result buffer), so the
 // upload of stripe s+1 overlaps the stacking of stripe s and the download of stripe s-1 -- the device never holds more
@@ -380,16 +398,8 @@ static int stack_apply_range(nl_ctx *ctx, const float *const *host_frames, int32
         return r;
     };
     for (int l = 0; l < lanes && rc == NL_OK; l++) {
-        if (!ctx->lane_ctx[l]) {
-            rc = nl_ctx_create(ctx->device, &ctx->lane_ctx[l]);
-            if (rc == NL_OK) {                               // the lanes inherit the tuning of their context
-                nl_ctx *lc = ctx->lane_ctx[l];
-                lc->defer_override = ctx->defer_override; lc->defer_n = ctx->defer_n;
-                for (int i = 0; i < 8; i++) lc->defer_at[i] = ctx->defer_at[i];
-                lc->tile_width = ctx->tile_width;
-                lc->linfit_stream = ctx->linfit_stream; lc->linfit_stream_ctas = ctx->linfit_stream_ctas; lc->linfit_stream_cache = ctx->linfit_stream_cache;
-            }
-        }
+        nl_ctx *lc = nullptr;
+        rc = lane_context(ctx, l, &lc);
         if (rc == NL_OK && (lane_px > ctx->lane_px[l] || n_frames != ctx->lane_frames[l] || !ctx->lane_job[l])) {   // (re)size the lane
             if (ctx->lane_job[l]) { nl_stack_end(ctx->lane_job[l]); ctx->lane_job[l] = nullptr; }
             if (ctx->lane_out[l]) { nl_dev_free(ctx->lane_ctx[l], ctx->lane_out[l]); ctx->lane_out[l] = nullptr; }
