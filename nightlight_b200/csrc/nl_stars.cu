@@ -28,6 +28,27 @@
 
 namespace nl {
 
+__host__ __device__ static inline void cswap(float &a, float &b) { if (a > b) { float t = a; a = b; b = t; } }
+
+// MedianFloat32Slice9, median3x3.go:85-110 (the partially sorted buffer is an observable side effect)
+__host__ __device__ static inline float median9(float *a) {
+    cswap(a[0], a[1]); cswap(a[3], a[4]); cswap(a[6], a[7]);
+    cswap(a[1], a[2]); cswap(a[4], a[5]); cswap(a[7], a[8]);
+    cswap(a[0], a[1]); cswap(a[3], a[4]); cswap(a[6], a[7]);
+    if (a[0] > a[3]) a[3] = a[0];
+    if (a[3] > a[6]) a[6] = a[3];
+    cswap(a[1], a[4]);
+    if (a[4] > a[7]) a[4] = a[7];
+    if (a[1] > a[4]) a[4] = a[1];
+    if (a[5] > a[8]) a[5] = a[8];
+    if (a[2] > a[5]) a[2] = a[5];
+    cswap(a[2], a[4]);
+    if (a[4] > a[6]) a[4] = a[6];
+    if (a[2] > a[4]) a[4] = a[2];
+    return a[4];
+}
+
+
 template <bool WRITE>
 __global__ void __launch_bounds__(256) bright_rows_kernel(const float *__restrict__ data, int len, int width, int rows,
                                                           float threshold, int radius, int *__restrict__ row_count,
@@ -220,9 +241,15 @@ __global__ void __launch_bounds__(1024) row_offsets_batch_kernel(const int *__re
     if (threadIdx.x == 0) { totals[blockIdx.x] = carry; overflow[blockIdx.x] = over; }
 }
 
+// With bp_thr (one threshold per frame): rejectBadPixels' test (findstars.go:134-169) for every candidate whose 3x3
+// neighbourhood lies inside the frame -- flag 1: keep, 0: reject -- while the candidate is at hand; flag 2 marks the
+// candidates of the first and last row, whose gather buffer keeps entries of the candidate before them (the host
+// replays those).
 __global__ void __launch_bounds__(256) bright_compact_kernel(const nl_star *__restrict__ slots, const int *__restrict__ row_count,
                                                              const int *__restrict__ row_offset, int rows, nl_star *__restrict__ list,
-                                                             long long list_stride) {
+                                                             long long list_stride, const float *__restrict__ frames,
+                                                             long long frame_stride, int len, int width,
+                                                             const float *__restrict__ bp_thr, unsigned char *__restrict__ flags) {
     // one warp per row: lane i moves candidate i of the row to the frame's list (frames with overflowing rows are redone)
     const int lane = threadIdx.x & 31;
     const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
@@ -231,7 +258,27 @@ __global__ void __launch_bounds__(256) bright_compact_kernel(const nl_star *__re
     const int c = row_count[fr];
     if (lane < c && lane < BRIGHT_SLOTS) {
         const long long dst = (long long)row_offset[fr] + lane;
-        if (dst < list_stride) list[(long long)blockIdx.y * list_stride + dst] = slots[fr * BRIGHT_SLOTS + lane];
+        if (dst < list_stride) {
+            const nl_star s = slots[fr * BRIGHT_SLOTS + lane];
+            list[(long long)blockIdx.y * list_stride + dst] = s;
+            if (bp_thr) {
+                unsigned char flag = 2;
+                const long long idx = s.index;
+                if (idx - width - 1 >= 0 && idx + width + 1 < len) {
+                    const float *d = frames + (long long)blockIdx.y * frame_stride;
+                    float b[9];
+#pragma unroll
+                    for (int y = -1; y <= 1; y++)
+#pragma unroll
+                        for (int x = -1; x <= 1; x++) b[(y + 1) * 3 + (x + 1)] = d[idx + (long long)y * width + x];
+                    const float med = median9(b);
+                    const float diff = d[idx] - med;
+                    const float thr = bp_thr[blockIdx.y];
+                    flag = (diff < thr && -diff < thr) ? 1 : 0;
+                }
+                flags[(long long)blockIdx.y * list_stride + dst] = flag;
+            }
+        }
     }
 }
 
@@ -426,26 +473,6 @@ static std::vector<int32_t> create_mask(int32_t width, float radius) {
     return mask;
 }
 
-static inline void cswap(float &a, float &b) { if (a > b) { float t = a; a = b; b = t; } }
-
-// MedianFloat32Slice9, median3x3.go:85-110 (the partially sorted buffer is an observable side effect)
-static float median9(float *a) {
-    cswap(a[0], a[1]); cswap(a[3], a[4]); cswap(a[6], a[7]);
-    cswap(a[1], a[2]); cswap(a[4], a[5]); cswap(a[7], a[8]);
-    cswap(a[0], a[1]); cswap(a[3], a[4]); cswap(a[6], a[7]);
-    if (a[0] > a[3]) a[3] = a[0];
-    if (a[3] > a[6]) a[6] = a[3];
-    cswap(a[1], a[4]);
-    if (a[4] > a[7]) a[4] = a[7];
-    if (a[1] > a[4]) a[4] = a[1];
-    if (a[5] > a[8]) a[5] = a[8];
-    if (a[2] > a[5]) a[2] = a[5];
-    cswap(a[2], a[4]);
-    if (a[4] > a[6]) a[4] = a[6];
-    if (a[2] > a[4]) a[4] = a[2];
-    return a[4];
-}
-
 // rejectBadPixels with medianDiffStats given, findstars.go:134-169.  GatherAndMedian (gather.go:26-38)
 // takes the median of the WHOLE 9-entry buffer even when fewer neighbours were in range, so entries
 // left over from the previous candidate take part at the image borders; the buffer persists here too.
@@ -469,6 +496,40 @@ static int reject_bad_pixels(nl_star *stars, int n, const float *data, int32_t l
     return remaining;
 }
 
+// rejectBadPixels with the test of the interior candidates done on the device (bright_compact_kernel): flag 1 keeps,
+// 0 rejects, 2 = a candidate of the first or last row.  Its gather buffer is only partly overwritten, so the verdict
+// depends on what the candidate before it left there: replayed from the last candidate that filled the whole buffer.
+static int reject_bad_pixels_flagged(nl_star *stars, int n, const unsigned char *flags, const float *data, int32_t len, int32_t width,
+                                     float sigma, float median_diff_stddev) {
+    const std::vector<int32_t> mask = create_mask(width, 1.5f);
+    const float threshold = median_diff_stddev * sigma;
+    int remaining = 0;
+    std::vector<int32_t> chain;          // the last candidate that filled the whole buffer and the first/last-row candidates since
+    for (int i = 0; i < n; i++) {
+        const int32_t idx = stars[i].index;
+        bool keep = flags[i] == 1;
+        if (flags[i] == 2) {
+            chain.push_back(idx);
+            float buffer[16] = {0};
+            for (int32_t c : chain) {
+                int num = 0;
+                for (int32_t o : mask) {
+                    const int32_t io = c + o;
+                    if (io >= 0 && io < len) buffer[num++] = data[io];
+                }
+                const float med = median9(buffer);
+                const float diff = data[c] - med;
+                keep = diff < threshold && -diff < threshold;
+            }
+        } else {
+            chain.clear();
+            chain.push_back(idx);
+        }
+        if (keep) stars[remaining++] = stars[i];
+    }
+    return remaining;
+}
+
 // pre.MedianFilterSparse, badpixels.go:79-85: the listed pixels are replaced one after the other, in place, by the
 // median of their radius-1.5 neighbourhood (a repaired pixel is seen by the repairs after it); sparse, host side
 void median_filter_sparse_host(float *data, int32_t len, int32_t width, const int32_t *indices, int64_t n) {
@@ -485,8 +546,11 @@ void median_filter_sparse_host(float *data, int32_t len, int32_t width, const in
     }
 }
 
-// QSortStarsDesc, star/qsort.go:25-55: unstable Hoare quicksort by mass, descending
-static void qsort_stars_desc(nl_star *a, int n) {
+// QSortStarsDesc, star/qsort.go:25-55: unstable Hoare quicksort by mass, descending.  The order it leaves equal masses
+// in is part of the result (the overlap filter keeps greedily in that order), so it is this algorithm, step for step --
+// run on (mass, position) keys of 8 bytes instead of the 32-byte records, which then move once.
+struct StarKey { float mass; int pos; };
+static void qsort_keys_desc(StarKey *a, int n) {
     while (n > 1) {
         const float pivot = a[(n - 1) >> 1].mass;
         int l = -1, r = n;
@@ -494,17 +558,25 @@ static void qsort_stars_desc(nl_star *a, int n) {
             do l++; while (a[l].mass > pivot);
             do r--; while (a[r].mass < pivot);
             if (l >= r) break;
-            const nl_star t = a[l]; a[l] = a[r]; a[r] = t;
+            const StarKey t = a[l]; a[l] = a[r]; a[r] = t;
         }
-        qsort_stars_desc(a, r + 1);     // left part recursively, right part iteratively
+        qsort_keys_desc(a, r + 1);      // left part recursively, right part iteratively
         a += r + 1;
         n -= r + 1;
     }
 }
+static void qsort_stars_desc(nl_star *a, int n) {
+    if (n < 2) return;
+    std::vector<StarKey> keys((size_t)n);
+    for (int i = 0; i < n; i++) keys[i] = StarKey{a[i].mass, i};
+    qsort_keys_desc(keys.data(), n);
+    std::vector<nl_star> tmp(a, a + n);
+    for (int i = 0; i < n; i++) a[i] = tmp[keys[i].pos];
+}
 
 // filterOutOverlaps, findstars.go:209-271: greedy keep in the given order; 256 px bins, each a list
 // in insertion order
-static int filter_out_overlaps(nl_star *stars, int n, int32_t width, int32_t height, int32_t radius) {
+static int filter_out_overlaps_bins256(nl_star *stars, int n, int32_t width, int32_t height, int32_t radius) {
     const int32_t bin = 256;
     const int32_t xbins = (width + bin - 1) / bin, ybins = (height + bin - 1) / bin;
     std::vector<std::vector<int>> bins((size_t)(xbins > 0 && ybins > 0 ? xbins * ybins : 0));
@@ -530,6 +602,53 @@ static int filter_out_overlaps(nl_star *stars, int n, int32_t width, int32_t hei
         // the reference indexes its bin table unguarded here (findstars.go:255) and would panic for a
         // star whose centre left the image; such a star is kept but not binned
         if (xc >= 0 && xc < xbins && yc >= 0 && yc < ybins) bins[(size_t)(xc + yc * xbins)].push_back(kept);
+        kept++;
+    }
+    return kept;
+}
+
+// The same filter on a finer grid.  A candidate is dropped when a star kept (and binned) before it has
+// int32(dx^2 + dy^2 + 0.5) <= radius^2, i.e. lies closer than radius + 1 in x and in y; the reference finds such a star
+// because it is in the same or an adjacent 256-pixel bin.  With cells of at least radius + 1 pixels it is just as
+// surely in the same or an adjacent cell, so scanning 3 x 3 cells gives the same verdict for every candidate -- over a
+// handful of stars instead of the hundreds a 256-pixel bin of a dense candidate list holds (the scan of a frame's
+// ~20 000 candidates was the largest host step of the batched star detection).  Which star matches does not matter,
+// only whether one does; a star the reference does not bin (centre outside the image) is not binned here either.
+static int filter_out_overlaps(nl_star *stars, int n, int32_t width, int32_t height, int32_t radius) {
+    const int32_t bin = 256;
+    if (radius < 0 || radius + 1 > bin / 2 || width <= 0 || height <= 0) return filter_out_overlaps_bins256(stars, n, width, height, radius);
+    const int32_t xbins = (width + bin - 1) / bin, ybins = (height + bin - 1) / bin;
+    const int32_t cs = radius + 1 > 16 ? radius + 1 : 16;                         // cell size in pixels
+    // a binned star has int32(x + 0.5) in (-256, xbins*256): shifted by 256 its cell index is >= 0
+    const int32_t xcells = (xbins * bin + bin) / cs + 1, ycells = (ybins * bin + bin) / cs + 1;
+    std::vector<int> head((size_t)xcells * ycells, -1), next((size_t)n, -1);
+    auto floordiv = [](long long a, long long b) { return (a >= 0 ? a / b : -((-a + b - 1) / b)); };
+    const int32_t r2 = radius * radius;
+    int kept = 0;
+    for (int i = 0; i < n; i++) {
+        const nl_star s = stars[i];
+        const int32_t xi = (int32_t)(s.x + 0.5f), yi = (int32_t)(s.y + 0.5f);
+        const long long cx = floordiv((long long)xi + bin, cs), cy = floordiv((long long)yi + bin, cs);
+        bool skip = false;
+        for (long long yy = cy - 1; yy <= cy + 1 && !skip; yy++) {
+            if (yy < 0 || yy >= ycells) continue;
+            for (long long xx = cx - 1; xx <= cx + 1 && !skip; xx++) {
+                if (xx < 0 || xx >= xcells) continue;
+                for (int j = head[(size_t)(xx + yy * xcells)]; j >= 0; j = next[j]) {
+                    const float xd = s.x - stars[j].x, yd = s.y - stars[j].y;
+                    const int32_t sq = (int32_t)(xd * xd + yd * yd + 0.5f);
+                    if (sq <= r2) { skip = true; break; }
+                }
+            }
+        }
+        if (skip) continue;
+        stars[kept] = s;
+        const int32_t xc = xi / bin, yc = yi / bin;                                 // the reference's bin (findstars.go:255)
+        if (xc >= 0 && xc < xbins && yc >= 0 && yc < ybins) {
+            const size_t cell = (size_t)(cx + cy * xcells);
+            next[kept] = head[cell];
+            head[cell] = kept;
+        }
         kept++;
     }
     return kept;
@@ -713,17 +832,21 @@ namespace nl {
 // frame and two host round trips in total: per-row slots, scan of the row counts, compaction into raster order straight
 // into mapped pinned host memory.  On return frame i's first min(counts[i], keep_cap) candidates are at *list + i * *stride
 // (host memory owned by the context, valid until the next batched scan).
+// bp_thresholds (optional, per frame): the compaction also runs rejectBadPixels' test; *flags = its result per candidate
+// ([frame][stride], see bright_compact_kernel), flags_valid[i] = 0 for a frame that was redone by the two-pass scan.
 static int bright_scan_batch(nl_ctx *ctx, const float *dev_frames, int n_frames, long long frame_stride, int len, int width,
-                             const float *thresholds, int radius, int keep_cap, nl_star **list, long long *stride, int32_t *counts) {
+                             const float *thresholds, int radius, int keep_cap, nl_star **list, long long *stride, int32_t *counts,
+                             const float *bp_thresholds = nullptr, unsigned char **flags = nullptr, std::vector<char> *flags_valid = nullptr) {
     const int rows = (len + width - 1) / width;
     const size_t fr = (size_t)n_frames * rows;
     // scratch: row counts | row offsets | thresholds | totals | overflow ; ctx->list: the row slots
-    const size_t ints = 2 * fr + 3 * (size_t)n_frames;
+    const size_t ints = 2 * fr + 4 * (size_t)n_frames;
     int rc = ensure_scratch(ctx, (ints * sizeof(int) + 255) & ~(size_t)255);
     if (rc != NL_OK) return rc;
     int *row_count = (int *)ctx->scratch, *row_offset = row_count + fr;
     float *dthr = (float *)(row_offset + fr);
     int *totals = (int *)(dthr + n_frames), *overflow = totals + n_frames;
+    float *dbp = (float *)(overflow + n_frames);
     const size_t slot_bytes = fr * BRIGHT_SLOTS * sizeof(nl_star);
     if (ctx->list_bytes < slot_bytes) {
         if (ctx->list) { NL_CUDA(cudaStreamSynchronize(ctx->stream)); NL_CUDA(cudaFree(ctx->list)); ctx->list = nullptr; ctx->list_bytes = 0; }
@@ -739,12 +862,15 @@ static int bright_scan_batch(nl_ctx *ctx, const float *dev_frames, int n_frames,
         ctx->batch_pinned_bytes = bytes;
         return NL_OK;
     };
-    const size_t head = (2 * sizeof(int) * (size_t)n_frames + sizeof(float) * (size_t)n_frames + 255) & ~(size_t)255;   // totals | overflow | thresholds
-    rc = ensure_batch_pinned(head + sizeof(nl_star) * (size_t)n_frames * 4096);
+    const size_t head = (2 * sizeof(int) * (size_t)n_frames + 2 * sizeof(float) * (size_t)n_frames + 255) & ~(size_t)255;   // totals | overflow | thresholds | bad-pixel thresholds
+    const size_t per_cand = sizeof(nl_star) + 1;                      // a record and its flag
+    rc = ensure_batch_pinned(head + per_cand * (size_t)n_frames * 4096 + 256);
     if (rc != NL_OK) return rc;
-    memcpy((char *)ctx->batch_pinned + 2 * sizeof(int) * (size_t)n_frames, thresholds, sizeof(float) * (size_t)n_frames);
-    NL_CUDA(cudaMemcpyAsync(dthr, (char *)ctx->batch_pinned + 2 * sizeof(int) * (size_t)n_frames, sizeof(float) * (size_t)n_frames,
-                            cudaMemcpyHostToDevice, ctx->stream));
+    float *h_thr = (float *)((char *)ctx->batch_pinned + 2 * sizeof(int) * (size_t)n_frames);
+    memcpy(h_thr, thresholds, sizeof(float) * (size_t)n_frames);
+    if (bp_thresholds) memcpy(h_thr + n_frames, bp_thresholds, sizeof(float) * (size_t)n_frames);
+    NL_CUDA(cudaMemcpyAsync(dthr, h_thr, sizeof(float) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    if (bp_thresholds) NL_CUDA(cudaMemcpyAsync(dbp, h_thr + n_frames, sizeof(float) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256, wpc = threads / 32;
     dim3 grid((unsigned)((rows + wpc - 1) / wpc), (unsigned)n_frames);
     bright_rows_slots_kernel<<<grid, threads, 0, ctx->stream>>>(dev_frames, frame_stride, len, width, rows, dthr, radius, row_count, slots);
@@ -762,11 +888,16 @@ static int bright_scan_batch(nl_ctx *ctx, const float *dev_frames, int n_frames,
         const int keep = host_tot[i] < keep_cap ? host_tot[i] : keep_cap;
         if (keep > max_keep) max_keep = keep;
     }
-    rc = ensure_batch_pinned(head + sizeof(nl_star) * (size_t)n_frames * max_keep);
+    rc = ensure_batch_pinned(head + per_cand * (size_t)n_frames * max_keep + 256);
     if (rc != NL_OK) return rc;
     nl_star *host_list = (nl_star *)((char *)ctx->batch_pinned + head);
     nl_star *dev_list = (nl_star *)((char *)ctx->batch_pinned_dev + head);
-    bright_compact_kernel<<<grid, threads, 0, ctx->stream>>>(slots, row_count, row_offset, rows, dev_list, max_keep);
+    const size_t flags_off = head + sizeof(nl_star) * (size_t)n_frames * max_keep;
+    bright_compact_kernel<<<grid, threads, 0, ctx->stream>>>(slots, row_count, row_offset, rows, dev_list, max_keep, dev_frames, frame_stride,
+                                                             len, width, bp_thresholds ? dbp : nullptr,
+                                                             (unsigned char *)ctx->batch_pinned_dev + flags_off);
+    if (flags) *flags = (unsigned char *)ctx->batch_pinned + flags_off;
+    if (flags_valid) flags_valid->assign((size_t)n_frames, bp_thresholds ? 1 : 0);
     NL_CUDA(cudaGetLastError());
     ctx->launches++;
     NL_CUDA(cudaStreamSynchronize(ctx->stream));                       // round trip 2: the candidates have landed in host memory
@@ -779,9 +910,11 @@ static int bright_scan_batch(nl_ctx *ctx, const float *dev_frames, int n_frames,
         if (rc != NL_OK) return rc;
         if (n > max_keep && max_keep < keep_cap) {
             // (the recount found more than the slots let the first pass see: grow the lists and redo the whole batch)
-            return bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thresholds, radius, keep_cap, list, stride, counts);
+            return bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thresholds, radius, keep_cap, list, stride, counts,
+                                     bp_thresholds, flags, flags_valid);
         }
         counts[i] = n;
+        if (flags_valid) (*flags_valid)[i] = 0;
     }
     *list = host_list;
     *stride = max_keep;
@@ -855,7 +988,15 @@ int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fram
     std::vector<int32_t> m((size_t)n_frames);
     nl_star *list = nullptr;
     long long stride = 0;
-    int rc = bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, 0x7fffffff, &list, &stride, m.data());
+    std::vector<float> bp_thr;
+    if (bp_sigma > 0) {
+        bp_thr.resize((size_t)n_frames);
+        for (int i = 0; i < n_frames; i++) bp_thr[i] = median_diff_stddev[i] * bp_sigma;         // findstars.go:137
+    }
+    unsigned char *flags = nullptr;
+    std::vector<char> flags_valid;
+    int rc = bright_scan_batch(ctx, dev_frames, n_frames, frame_stride, len, width, thr.data(), radius, 0x7fffffff, &list, &stride, m.data(),
+                               bp_sigma > 0 ? bp_thr.data() : nullptr, &flags, &flags_valid);
     if (rc != NL_OK) return rc;
     nl_star *dev_list = (nl_star *)((char *)ctx->batch_pinned_dev + ((char *)list - (char *)ctx->batch_pinned));
     t_dev += since(t0);
@@ -865,11 +1006,15 @@ int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fram
     each_frame([&](int i) {
         nl_star *st = list + (size_t)i * stride;
         int k = m[i];
-        if (bp_sigma > 0) k = reject_bad_pixels(st, k, host_frames[i], len, width, bp_sigma, median_diff_stddev[i]);
+        if (bp_sigma > 0) {
+            if (flags_valid[i]) k = reject_bad_pixels_flagged(st, k, flags + (size_t)i * stride, host_frames[i], len, width, bp_sigma, median_diff_stddev[i]);
+            else k = reject_bad_pixels(st, k, host_frames[i], len, width, bp_sigma, median_diff_stddev[i]);
+        }
         qsort_stars_desc(st, k);
         m[i] = filter_out_overlaps(st, k, width, len / width, radius);
     });
     t_host += since(t0);
+    if (ctx->stats_debug) fprintf(stderr, "find_stars_batch: %d host threads, reject+sort+overlaps %.3f ms\n", n_threads, since(t0) * 1e3);
 
     // ---- device: shiftToCenterOfMass.  Per-frame scalars and per-star outputs in a second pinned block.
     t0 = clk::now();
@@ -911,6 +1056,7 @@ int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fram
         m[i] = filter_out_overlaps(st, m[i], width, len / width, radius);
     });
     t_host += since(t0);
+    if (ctx->stats_debug) fprintf(stderr, "find_stars_batch: shifts+sort+overlaps %.3f ms\n", since(t0) * 1e3);
 
     // ---- device: calcAndFilterHalfFluxRadius
     t0 = clk::now();
@@ -944,6 +1090,7 @@ int nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fram
         for (int k = 0; k < remaining && k < cap; k++) out[(size_t)i * cap + k] = st[k];
     });
     t_host += since(t0);
+    if (ctx->stats_debug) fprintf(stderr, "find_stars_batch: survivors %.3f ms\n", since(t0) * 1e3);
     if (seconds_device) *seconds_device = t_dev;
     if (seconds_host) *seconds_host = t_host;
     return NL_OK;

@@ -375,6 +375,15 @@ def test_batched_star_scan_one_read_per_frame(ctx):
     w, h, n = 640, 300, 6
     frames = np.stack([star_field(w, h, 60, seed=100 + k) for k in range(n)])
     frames[3].reshape(h, w)[17, ::9] += 4000.0          # 72 isolated hits in one row (radius 4): beyond the 32 slots
+    # candidates in the first and last row and at both ends of the frame: rejectBadPixels' gather buffer keeps entries of
+    # the candidate before them there (the device tests the interior candidates, the host replays these)
+    frames[1].reshape(h, w)[0, 5::40] += 3000.0
+    frames[1].reshape(h, w)[h - 1, 7::37] += 3000.0
+    frames[2].ravel()[0] += 5000.0
+    frames[2].ravel()[-1] += 5000.0
+    frames[2].reshape(h, w)[0, 100:300:11] += 900.0
+    frames[4].reshape(h, w)[h - 1, 3::23] += 2500.0
+    frames[4].reshape(h, w)[h - 2, 9::29] += 2500.0
     radius = 4
     thr = np.array([130.0 + k for k in range(n)], np.float32)
     job, base, stride = _resident(ctx, frames)

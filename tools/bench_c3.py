@@ -93,6 +93,9 @@ def run_c3(args):
     lib = nl.load_library()
     torch.cuda.set_device(0)
     ctx = nl.Context(0)
+    for kv in [x for x in (getattr(args, "tune", "") or "").split(",") if x]:      # nl_ctx_set_tuning knobs (A/B measurements)
+        k, v = kv.split("=", 1)
+        ctx.set_tuning(k, v.replace(":", ","))
     ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", 0))
     fp = C.POINTER(C.c_float)
 
