@@ -10,6 +10,7 @@
 #include "../../include/nightlight_cuda.h"
 
 #define NL_MAX_PEERS 8
+#define NL_MAX_LANES 5       // helper contexts (stream + scratch) a context keeps on its device
 #define NL_JOB_COUNTERS 32     // device counters of a stack job: clip low/high, tile counter, two per deferral round
 
 struct nl_ctx {
@@ -36,7 +37,7 @@ struct nl_ctx {
     size_t list_bytes = 0;
     // nl_stack_apply keeps its two stripe lanes (context + job + result buffer each) between calls:
     // allocating and freeing multi-GiB device buffers per call would cost more than the stack itself
-    nl_ctx *lane_ctx[2] = {nullptr, nullptr};
+    nl_ctx *lane_ctx[NL_MAX_LANES] = {nullptr};      // (the stripe lanes are the first two; the batched bad-pixel maps use all)
     struct nl_stack_job *lane_job[2] = {nullptr, nullptr};
     float *lane_out[2] = {nullptr, nullptr};
     int64_t lane_px[2] = {0, 0};

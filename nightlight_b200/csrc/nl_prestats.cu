@@ -791,11 +791,11 @@ int nl_bad_pixel_map_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_f
     NL_REQUIRE(dev_frames || n_frames == 0, "NULL frames");
     NL_REQUIRE(frame_stride % 4 == 0 && ((uintptr_t)dev_frames & 15) == 0, "frames must start on 16 bytes");
     NL_GUARD(ctx);
-    // three frames in flight: the context and its two lanes (own stream, scratch and pinned read-back buffers each),
-    // one host thread per lane -- a frame's chain is a handful of short kernels and two host round trips, which the
-    // other two lanes fill
-    constexpr int WORKERS = 3;
-    nl_ctx *wc[WORKERS] = {ctx, nullptr, nullptr};
+    // several frames in flight: the context and its lanes (own stream, scratch and pinned read-back buffers each), one
+    // host thread per lane -- a frame's chain is a handful of short kernels and two host round trips, which the other
+    // lanes fill
+    constexpr int WORKERS = 1 + NL_MAX_LANES;
+    nl_ctx *wc[WORKERS] = {ctx};
     const int workers = n_frames < WORKERS ? (n_frames < 1 ? 1 : n_frames) : WORKERS;
     for (int w = 1; w < workers; w++) {
         int rc = lane_context(ctx, w - 1, &wc[w]);
@@ -803,8 +803,8 @@ int nl_bad_pixel_map_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_f
     }
     NL_CUDA(cudaStreamSynchronize(ctx->stream));          // the frames were produced on the context's stream
     std::atomic<int> next{0};
-    int64_t replays_of_lanes[WORKERS] = {0, 0, 0};
-    int rcs[WORKERS] = {NL_OK, NL_OK, NL_OK};
+    int64_t replays_of_lanes[WORKERS] = {0};
+    int rcs[WORKERS] = {NL_OK};
     std::string msgs[WORKERS];
     auto work = [&](int w) {
         nl_ctx *c = wc[w];

@@ -505,6 +505,8 @@ int nl_stack_apply_release(nl_ctx *ctx) {
         if (ctx->lane_ctx[l]) { nl_ctx_destroy(ctx->lane_ctx[l]); ctx->lane_ctx[l] = nullptr; }
         ctx->lane_px[l] = 0; ctx->lane_frames[l] = 0;
     }
+    for (int l = 2; l < NL_MAX_LANES; l++)
+        if (ctx->lane_ctx[l]) { nl_ctx_destroy(ctx->lane_ctx[l]); ctx->lane_ctx[l] = nullptr; }
     return NL_OK;
 }
 
