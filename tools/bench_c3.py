@@ -309,3 +309,204 @@ def run_c3(args):
     lib.nl_host_free_pinned(host)
     ctx.close()
     return 0
+
+
+def run_c3_multi(args):
+    """configs[2] on N GPUs of one box: detection and resampling shard over FRAMES (rank r owns frames
+    r, r+N, ...), the stack over ROW STRIPES; the exchange between the two is fused into the resample's stores
+    (nl_project_scatter_dev writes every destination row into the peer-mapped stack job of the rank that owns it).
+    One step = bad-pixel statistics + FindStars of the local frames, scatter-resample, barrier, linear-fit stack of the
+    local stripe, all-gather of the stripes.  Launched by torchrun; rank 0 prints the line."""
+    import torch
+    import torch.distributed as dist
+    import nightlight_b200 as nl
+    from nightlight_b200 import stripes
+    from bench import ClockSampler, peaks, source_hash, UNIT
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    lib = nl.load_library()
+    ctx = nl.Context(local)
+    fp = C.POINTER(C.c_float)
+    n, w, h = N, W, H
+    if args.rows:
+        h = args.rows
+    px = w * h
+    ids = stripes.frame_shard(n, world, rank)
+    m = len(ids)
+    trans = poses(n)
+    stars = star_list(2500 * h // H + 50, w=w, h=h)
+
+    # ---- this rank's frames in pinned host memory, then resident
+    t0 = time.perf_counter()
+    host = C.c_void_p()
+    nl.binding.check(lib.nl_host_alloc_pinned(4 * m * px, C.byref(host)))
+    frames = np.ctypeslib.as_array(C.cast(host, fp), shape=(m, px))
+    cores = max(1, (os.cpu_count() or 1) // world)
+
+    def work(i0):
+        for i in range(i0, m, cores):
+            frames[i] = render_frame(ids[i], trans[ids[i]], stars, w, h)
+
+    th = [threading.Thread(target=work, args=(i0,)) for i0 in range(min(cores, m))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    gen_s = time.perf_counter() - t0
+    raw = ctx.dev_alloc(4 * m * px)
+
+    def upload():
+        nl.binding.check(lib.nl_memcpy_h2d(ctx.handle, C.c_void_p(raw), host, 4 * m * px))
+
+    sc = stripes.PeerScatter(ctx, nl.StackJob, n, w, h)
+    row0, rows = sc.row0, sc.rows
+    out_stripe = torch.empty(rows * w, dtype=torch.float32, device=dev)
+    loc = np.full(m, BACKGROUND, np.float32)
+    scale = np.full(m, NOISE, np.float32)
+    cap = 20000
+    found = np.zeros((m, cap), dtype=nl.STAR_DTYPE)
+    counts = np.zeros(m, np.int32)
+    sos, hfr = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    bcounts = np.zeros(m, np.int64)
+    bstats = np.zeros((m, 4), np.float32)
+    ptrs = (C.c_void_p * m)(*[host.value + 4 * i * px for i in range(m)])
+    mode = lib.nl_auto_select_mode(n)
+    state = {}
+
+    def step(seg):
+        t = time.perf_counter()
+        nl.binding.check(lib.nl_bad_pixel_map_batch_dev(ctx.handle, C.c_void_p(raw), m, px, px, w, 3.0, 5.0, None, 0,
+                                                        bcounts.ctypes.data_as(C.POINTER(C.c_int64)), bstats.ctypes.data_as(fp)))
+        mds = np.ascontiguousarray(bstats[:, 3])
+        td, thost = C.c_double(), C.c_double()
+        nl.binding.check(lib.nl_find_stars_batch_dev(ctx.handle, C.c_void_p(raw), m, px, ptrs, px, w, loc.ctypes.data_as(fp),
+                                                     scale.ctypes.data_as(fp), STAR_SIG, BP_SIGMA, IN_OUT, RADIUS, mds.ctypes.data_as(fp),
+                                                     found.ctypes.data_as(C.c_void_p), cap, counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     sos.ctypes.data_as(fp), hfr.ctypes.data_as(fp), C.byref(td), C.byref(thost)))
+        t1 = time.perf_counter()
+        for i, k in enumerate(ids):
+            sc.project(raw + 4 * i * px, w, h, k, trans[k])
+        sc.finish()                                   # every rank's rows have landed in every job
+        t2 = time.perf_counter()
+        sc.job.run_dev(mode, out_stripe.data_ptr(), None, 2.75, 2.75, 0.0)
+        ctx.sync()
+        t3 = time.perf_counter()
+        state["full"] = stripes.allgather_image(out_stripe, w, h)
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        seg["detect_ms"].append((t1 - t) * 1e3)
+        seg["scatter_resample_ms"].append((t2 - t1) * 1e3)
+        seg["stack_ms"].append((t3 - t2) * 1e3)
+        seg["gather_ms"].append((t4 - t3) * 1e3)
+        seg["total_ms"].append((t4 - t) * 1e3)
+
+    names = ["detect_ms", "scatter_resample_ms", "stack_ms", "gather_ms", "total_ms"]
+
+    def timed(fn, reps):
+        """median over reps of the slowest rank's wall clock around fn (barrier on both sides)"""
+        out = []
+        for _ in range(reps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            fn()
+            ms = torch.tensor([(time.perf_counter() - t) * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            out.append(float(ms.item()))
+        return float(np.median(out)), out
+
+    upload()
+    ctx.sync()
+    warm = {k: [] for k in names}
+    for _ in range(max(3, args.warmup) if not args.rows else 1):
+        dist.barrier()
+        step(warm)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    seg = {k: [] for k in names}
+    steps = args.steps
+    ms_step, _ = timed(lambda: step(seg), steps)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    med = {k: float(np.median(v)) for k, v in seg.items()}
+    host_full = np.empty(px, np.float32) if rank == 0 else None
+
+    def e2e_step():
+        upload()
+        step({k: [] for k in names})
+        if rank == 0:
+            ctx.sync()
+            host_full[:] = state["full"].cpu().numpy()
+
+    ms_e2e, _ = timed(e2e_step, max(1, min(steps, args.e2e_steps)))
+
+    # ---- parity on rank 0 (bounded CPU samples), and every rank's stripe arrived in the gathered image
+    mine = state["full"][row0 * w:(row0 + rows) * w]
+    ok_t = torch.tensor([1 if torch.equal(mine.view(torch.int32), out_stripe.view(torch.int32)) else 0], device=dev)
+    dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    parity = {}
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as O
+        i = 1 if m > 1 else 0
+        want = O.find_stars(frames[i], w, BACKGROUND, NOISE, STAR_SIG, BP_SIGMA, IN_OUT, RADIUS, float(bstats[i, 3]))
+        stars_ok = counts[i] == len(want[0]) and found[i, :counts[i]].tobytes() == want[0].tobytes()
+        jbase, jstride = sc.job.frames_dev
+
+        def stripe_of_frame(k, nrows):
+            a = np.empty(nrows * w, np.float32)
+            ctx.d2h(a, jbase + 4 * k * jstride)
+            return a
+
+        def same(a, b):
+            an, bn = np.isnan(a), np.isnan(b)
+            return bool(np.array_equal(an, bn) and np.array_equal(a.view(np.uint32)[~an], b.view(np.uint32)[~bn]))
+
+        # a frame this rank resampled itself and one that arrived from a peer (rendered again here for the CPU side)
+        k_own, k_peer = ids[i], (1 if world > 1 else ids[0])
+        proj_ok = True
+        for k in (k_own, k_peer):
+            src = frames[ids.index(k)] if k in ids else render_frame(k, trans[k], stars, w, h)
+            wantp = O.project(np.ascontiguousarray(src), w, h, w, h, trans[k], np.float32(np.nan))
+            proj_ok = proj_ok and same(stripe_of_frame(k, rows), wantp[row0 * w:(row0 + rows) * w])
+        srows = min(32, rows)
+        al = np.stack([stripe_of_frame(k, srows) for k in range(n)])
+        sw_, _, _ = O.stack(al, mode, 2.75, 2.75, threads=os.cpu_count() or 1)
+        stack_ok = same(out_stripe[:srows * w].cpu().numpy(), sw_)
+        parity = {"frame_checked": int(k_own), "stars_bit_exact": bool(stars_ok), "stars": int(counts[i]),
+                  "resample_bit_exact_own_and_peer_frame": [int(k_own), int(k_peer), bool(proj_ok)],
+                  "stack_rows_checked": srows, "stack_bit_exact": stack_ok, "stripes_in_gathered_image": bool(ok_t.item())}
+        if not (stars_ok and proj_ok and stack_ok and ok_t.item()):
+            raise SystemExit("c3 multi-GPU parity failure: %s" % json.dumps(parity))
+    if rank == 0:
+        peak, peak_src = peaks()
+        algo = 4.0 * (n + 1) * rows * w
+        line = {
+            "metric": METRIC, "value": n * px / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "star detection + resample sharded over frames (%d per GPU), linear-fit stack sharded over row stripes "
+                                   "(%d rows per GPU), %d x %dx%d fp32; the frame->stripe exchange is fused into the resample's stores "
+                                   "(peer-mapped stack jobs), stripes all-gathered with NCCL" % (m, rows, n, w, h),
+                       "config": "c3", "n_frames": n, "width": w, "height": h, "segments_ms_rank0": med, "mode": int(mode),
+                       "timing": "wall clock around the step, barrier before, max over ranks", "host_generation_s": gen_s,
+                       "parity": parity, "source_hash": source_hash()},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": algo / (med["stack_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (med["stack_ms"] * 1e-3) / 1e9 / peak, "traffic": None, "kernel_ms": med["stack_ms"],
+                         "kernel": "stack_column_kernel<linfit> on this rank's stripe", "algorithmic_bytes_per_launch": algo,
+                         "peak_source": peak_src},
+            "e2e": {"value": n * px / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * n * px,
+                    "d2h_bytes_per_step": 4 * px, "host_memory": "pinned",
+                    "api": "every rank uploads its frame shard (nl_memcpy_h2d), the step, rank 0 downloads the gathered image"},
+            "cpu_baseline": None, "gpu_launches": int(launches) * world,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    ctx.dev_free(raw)
+    sc.close()
+    lib.nl_host_free_pinned(host)
+    ctx.close()
+    dist.destroy_process_group()
+    return 0
