@@ -21,7 +21,8 @@ Other configurations (BASELINE.json configs[1..4]), same JSON contract:
   c4   1024 x 8192^2, linear-fit stacking, 1024-row stripes per GPU (8 GPUs = the whole image)
   c5   4096 x 4096^2, batches sized by OpStackBatches.partition from the device memory (capped at 256 frames per batch),
        sigma goal-seek on the first batch (count-only trial stacks), stack of stacks per stripe, one reassembly
-  c3   star detection + resample + stack over 64 x 6000x4000 resident frames (one GPU)
+  c3   star detection + resample + stack over 64 x 6000x4000 resident frames (one GPU; under torchrun: frame-sharded
+       detection and resample, fused scatter into row-stripe stack jobs, stack per stripe, all-gather)
 
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads, the reference's own 8 MiB
 work packages) on a bounded sample of the same workload; the Go reference itself cannot be built here (no Go

@@ -39,3 +39,14 @@ def test_scatter_resample_into_peer_stack_jobs():
 def test_two_gpu_bench_fused_gather_verified_against_nccl():
     d = _torchrun(["bench.py", "--gpus", "2", "--rows", "256", "--steps", "1", "--warmup", "3", "--no-e2e", "--no-cpu"], 29572)
     assert d["n_gpus"] == 2 and "verified against NCCL" in d["config"]["gather"]
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+def test_two_gpu_star_detect_resample_stack_pipeline():
+    """bench.py --config c3 under torchrun: detection and resample sharded over frames, fused scatter into the row-stripe
+    stack jobs (ragged stripes: 201 + 200 rows), stack per stripe, all-gather; the run itself compares stars, the stripe
+    rows of an own and of a peer's frame and the stacked rows with the CPU restatement and aborts on a difference"""
+    d = _torchrun(["bench.py", "--gpus", "2", "--config", "c3", "--rows", "401", "--steps", "1", "--warmup", "1"], 29573)
+    p = d["config"]["parity"]
+    assert d["n_gpus"] == 2 and p["stars_bit_exact"] and p["stack_bit_exact"] and p["stripes_in_gathered_image"]
+    assert p["resample_bit_exact_own_and_peer_frame"][2] is True
