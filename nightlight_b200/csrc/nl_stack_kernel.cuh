@@ -88,7 +88,10 @@ __device__ __forceinline__ void store_result(const StackArgs &a, long long p, fl
 // shared-memory bytes per column slot: the fp32 samples, the MAD scratch column, and (weighted
 // modes) the frame index of every sample.  (Measured: moving the index column to an L2-resident scratch in global
 // memory gives the weighted modes the seven warps per SM of the unweighted ones, but the clip loop's dependent
-// load/store pairs then wait on L2: sigma_w 10.4 -> 14.9 ms, winsor_w 14.9 -> 15.4 ms per 512-row stripe.  Rejected.)
+// load/store pairs then wait on L2: sigma_w 10.4 -> 14.9 ms, winsor_w 14.9 -> 15.4 ms per 512-row stripe.  Rejected.
+// Also measured: no index column at all, the moved slots kept as a (slot, position) table in the slots the clip loop
+// frees and the frames rebuilt in one walk per launch -- seven warps, bit-exact, but +23 % instructions in divergent
+// code: 9.8 / 13.1 ms at 256 frames, and 1.2-1.5 x SLOWER below 200 frames.  Rejected: profiles/r02_select_levers.md.)
 template <int MODE, bool W, typename IDX> struct SlotBytes {
     static constexpr int value = 4 * (MODE == ST_MAD ? 2 : 1) + (W ? (int)sizeof(IDX) : 0);
 };
