@@ -823,8 +823,16 @@ inline int launch_column(nl_stack_job *job, const StackArgs &args) {
 struct DeferSchedule { int n; int at[8]; double frac[2]; };
 inline DeferSchedule defer_schedule(int mode, const nl_ctx *ctx, int n_frames = 256) {
     DeferSchedule d{0, {0}, {0.25, 0.0}};
-    if (mode == ST_SIGMA) { d.n = 1; d.at[0] = 3; }
-    else if (mode == ST_WINSOR) { d.n = 1; d.at[0] = 2; }
+    if (mode == ST_SIGMA) {
+        // 256 frames: one regrouping after three passes.  Shorter columns settle earlier and profit from regrouping after
+        // every pass (same sample count, synthetic workload): 16 frames 7.48 -> 4.95 ms, 32 frames 5.96 -> 4.54 ms with
+        // {1,2,3}; 64 frames 4.97 -> 4.48 ms, 96 frames 4.80 -> 4.65 ms with {2,3,4}; from 128 frames on {3} wins
+        // (5.23 vs 5.43 ms).  The first pool of the short schedules takes every column (nearly all are still open).
+        if (n_frames <= 48) { d.n = 3; d.at[0] = 1; d.at[1] = 2; d.at[2] = 3; d.frac[0] = 1.0; d.frac[1] = 0.75; }
+        else if (n_frames <= 96) { d.n = 3; d.at[0] = 2; d.at[1] = 3; d.at[2] = 4; d.frac[0] = 1.0; d.frac[1] = 0.75; }
+        else { d.n = 1; d.at[0] = 3; }
+    }
+    else if (mode == ST_WINSOR) { d.n = 1; d.at[0] = 2; }     // (measured best or within 3 % of the best from 16 to 256 frames)
     else if (mode == ST_LINFIT) {
         // short columns need fewer rounds (a round rejects at least one sample, and there are fewer to reject), so
         // their columns are regrouped earlier and more often.  Measured on the synthetic workload, same sample count:
@@ -979,7 +987,8 @@ inline int launch_deferred(nl_stack_job *job, const StackArgs &args) {
         DeferSchedule d = defer_schedule(MODE, job->ctx, job->n);
         // several regrouping launches only pay with many tiles per warp (each launch ends in a tail of half-idle SMs):
         // measured, 1024 frames x 65 536 pixels: 15.5 ms in one launch, 16.6 ms with six regroupings; x 1 M pixels: 223 -> 213 ms
-        if (d.n > 1 && !job->ctx->defer_override && (job->pixels + S - 1) / S < 32ll * job->ctx->sm_count * 8) d.n = 0;
+        // (the clipping modes keep their first regrouping: one extra launch)
+        if (d.n > 1 && !job->ctx->defer_override && (job->pixels + S - 1) / S < 32ll * job->ctx->sm_count * 8) d.n = MODE == ST_LINFIT ? 0 : 1;
         StackArgs::Pool pools[2];
         if (d.n > 0 && ensure_pools(job, W ? (int)sizeof(IDX) : 0, d.frac, pools)) {
             StackArgs a2 = args;
