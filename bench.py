@@ -89,14 +89,15 @@ def source_hash():
 
 def stored_traffic(config, rows, n_gpus):
     """DRAM bytes per step of the stack kernels as measured by `bench.py --traffic` for THESE sources, else None"""
-    path = os.path.join(ROOT, "profiles", "traffic_%s.json" % config)
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        if t.get("source_hash") == source_hash() and t.get("rows") == rows:
-            return t.get("dram_bytes_per_step"), t
-    except Exception:
-        pass
+    # traffic_<config>.json: the whole image on one GPU; traffic_<config>_r<rows>.json: a row stripe (one rank of N)
+    for name in ("traffic_%s.json" % config, "traffic_%s_r%d.json" % (config, rows)):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            if t.get("source_hash") == source_hash() and t.get("rows") == rows:
+                return t.get("dram_bytes_per_step"), t
+        except Exception:
+            pass
     return None, None
 
 
@@ -875,7 +876,7 @@ def run_traffic(args, cfg):
     """runs `bench.py --traffic-child` under ncu (device-resident steps only), sums dram bytes over the stack kernels
     of ONE step and writes profiles/traffic_<config>.json keyed by the hash of the kernel sources"""
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    log = os.path.join(ROOT, "gpurun_out", "traffic_%s.csv" % args.config)
+    log = os.path.join(ROOT, "gpurun_out", "traffic_%s%s.csv" % (args.config, "_r%d" % args.rows if args.rows else ""))
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
            "-k", "regex:stack_column_kernel|stack_mean_kernel", "--csv", "--log-file", log,
            sys.executable, os.path.abspath(__file__), "--config", args.config, "--traffic-child", "--no-e2e", "--no-cpu",
@@ -912,7 +913,8 @@ def run_traffic(args, cfg):
            "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over `bench.py --traffic-child` (1 GPU)"}
     out["traffic_over_algorithmic"] = out["dram_bytes_per_step"] / out["algorithmic_bytes"]
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    with open(os.path.join(ROOT, "profiles", "traffic_%s.json" % args.config), "w") as f:
+    name = "traffic_%s_r%d.json" % (args.config, args.rows) if args.rows else "traffic_%s.json" % args.config
+    with open(os.path.join(ROOT, "profiles", name), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out))
     return 0
