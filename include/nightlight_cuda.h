@@ -303,6 +303,19 @@ int  nl_find_stars_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_fra
                              const float *median_diff_stddev, nl_star *out, int32_t cap, int32_t *counts,
                              float *sum_of_shifts, float *avg_hfr, double *seconds_device, double *seconds_host);
 
+/* The sparse, order-dependent steps of FindStars as the library runs them on host threads between its kernels, callable
+ * on their own (no device, no context): for callers that keep part of FindStars in Go, and for the CPU parity tests.
+ * nl_star_reject_bad_pixels_host: rejectBadPixels (findstars.go:134-169) the way the batched path runs it -- the test of
+ *   every candidate whose 3x3 neighbourhood lies inside the frame computed independently (the device's part), the
+ *   candidates of the first and last row replayed with the reference's carried-over gather buffer.
+ * nl_star_sort_desc_host: QSortStarsDesc (star/qsort.go:25-55), the reference's unstable quicksort step for step.
+ * nl_star_filter_overlaps_host: filterOutOverlaps (findstars.go:209-271), on the fine grid described in DESIGN.md 3.4.
+ * Each works in place; *kept = stars remaining. */
+int  nl_star_reject_bad_pixels_host(nl_star *stars, int32_t n, const float *data, int32_t len, int32_t width, float sigma,
+                                    float median_diff_stddev, int32_t *kept);
+int  nl_star_sort_desc_host(nl_star *stars, int32_t n);
+int  nl_star_filter_overlaps_host(nl_star *stars, int32_t n, int32_t width, int32_t height, int32_t radius, int32_t *kept);
+
 /* ---- synthetic frames (the workload generator, not reference code) --- */
 int  nl_synth_fill_dev(nl_ctx *ctx, float *dev_dst, uint64_t p0, int64_t count, uint32_t frame, uint32_t seed);
 

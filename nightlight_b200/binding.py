@@ -117,6 +117,9 @@ DECLARED_SYMBOLS = {
     "nl_find_stars_batch_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, C.POINTER(_vp), C.c_int32, C.c_int32, _fp, _fp, C.c_float,
                                          C.c_float, C.c_float, C.c_int32, _fp, _vp, C.c_int32, _i32p, _fp, _fp,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "nl_star_reject_bad_pixels_host": (C.c_int, [_vp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _i32p]),
+    "nl_star_sort_desc_host": (C.c_int, [_vp, C.c_int32]),
+    "nl_star_filter_overlaps_host": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p]),
     "nl_synth_fill_dev": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32]),
     "nl_dev_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "nl_dev_free": (C.c_int, [_vp, _vp]),

@@ -925,6 +925,42 @@ static int bright_scan_batch(nl_ctx *ctx, const float *dev_frames, int n_frames,
 
 extern "C" {
 
+// ---- the sparse host steps on their own (no device) ------------------------------------------------------------------
+int nl_star_reject_bad_pixels_host(nl_star *stars, int32_t n, const float *data, int32_t len, int32_t width, float sigma,
+                                   float median_diff_stddev, int32_t *kept) {
+    NL_REQUIRE(kept && n >= 0 && len >= 0 && width > 0 && (stars || n == 0) && (data || len == 0), "bad argument");
+    // the flags bright_compact_kernel writes: every candidate with its whole neighbourhood inside the frame on its own
+    std::vector<unsigned char> flags((size_t)n);
+    const float thr = median_diff_stddev * sigma;
+    for (int i = 0; i < n; i++) {
+        const long long idx = stars[i].index;
+        unsigned char flag = 2;
+        if (idx - width - 1 >= 0 && idx + width + 1 < len) {
+            float b[9];
+            for (int y = -1; y <= 1; y++)
+                for (int x = -1; x <= 1; x++) b[(y + 1) * 3 + (x + 1)] = data[idx + (long long)y * width + x];
+            const float med = median9(b);
+            const float diff = data[idx] - med;
+            flag = (diff < thr && -diff < thr) ? 1 : 0;
+        }
+        flags[i] = flag;
+    }
+    *kept = reject_bad_pixels_flagged(stars, n, flags.data(), data, len, width, sigma, median_diff_stddev);
+    return NL_OK;
+}
+
+int nl_star_sort_desc_host(nl_star *stars, int32_t n) {
+    NL_REQUIRE(n >= 0 && (stars || n == 0), "bad argument");
+    qsort_stars_desc(stars, n);
+    return NL_OK;
+}
+
+int nl_star_filter_overlaps_host(nl_star *stars, int32_t n, int32_t width, int32_t height, int32_t radius, int32_t *kept) {
+    NL_REQUIRE(kept && n >= 0 && (stars || n == 0), "bad argument");
+    *kept = filter_out_overlaps(stars, n, width, height, radius);
+    return NL_OK;
+}
+
 // findBrightPixels of all frames of a resident stack; host_out receives frame i's candidates at host_out + i*cap (the
 // first min(count, cap)); counts[i] = candidates found in frame i.
 int nl_find_bright_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int32_t len, int32_t width,
