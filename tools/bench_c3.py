@@ -186,7 +186,7 @@ def run_c3(args):
     # (bad-pixel statistics, star detection) of a chunk of frames run while the next chunk uploads on a second
     # context's stream; the resample and the stack need every frame.
     up = nl.Context(0)
-    chunk = max(1, n // 4)
+    chunk = max(1, n // 8)                               # (4 chunks: 161 ms, 8: 154 ms, 16: 155 ms)
     found2 = np.zeros((n, cap), dtype=nl.STAR_DTYPE)
     counts2 = np.zeros(n, np.int32)
     bstats2 = np.zeros((n, 4), np.float32)
