@@ -781,10 +781,10 @@ int nl_bad_pixel_map_dev(nl_ctx *ctx, const float *dev_data, int64_t len, int32_
     return set_error(NL_E_CUDA, "bad-pixel map: list did not fit after growing");
 }
 
-// BadPixelMap of every frame of a resident stack in one call (frame i at dev_frames + i*frame_stride): the frames are
-// processed one after the other on the context's stream -- their float64 statistics decide host-side whether a chain
-// must be replayed -- but the caller crosses the language boundary once.  stats = n_frames x 4, counts = n_frames,
-// host_bpm receives frame i's list at host_bpm + i*cap.
+// BadPixelMap of every frame of a resident stack in one call (frame i at dev_frames + i*frame_stride).  A frame's chain
+// stays what nl_bad_pixel_map_dev runs -- its float64 statistics decide host-side whether a chain must be replayed --
+// but up to six frames are in flight on the context's helper lanes, and the caller crosses the language boundary once.
+// stats = n_frames x 4, counts = n_frames, host_bpm receives frame i's list at host_bpm + i*cap.
 int nl_bad_pixel_map_batch_dev(nl_ctx *ctx, const float *dev_frames, int32_t n_frames, int64_t frame_stride, int64_t len, int32_t width,
                                float sigma_low, float sigma_high, int32_t *host_bpm, int64_t cap, int64_t *counts, float *stats) {
     NL_REQUIRE(ctx && counts && stats && n_frames >= 0, "bad argument");
