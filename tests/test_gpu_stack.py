@@ -535,3 +535,15 @@ def test_linear_fit_long_columns_streaming_rounds_and_in_place(ctx, tuning, stre
     check_against_oracle(ctx, frames, "linfit", False, 0.8, 0.8)
     frames2 = O.synth_frames(n, 31 * n, p)
     check_against_oracle(ctx, frames2, "linfit", False)
+
+
+@pytest.mark.parametrize("n", [16, 48, 64, 96, 97])
+def test_short_columns_built_in_regrouping_on_jobs_large_enough_to_use_it(ctx, n):
+    """columns of at most 96 frames are regrouped after every pass (sigma) / earlier and more often (linear fit) -- but only
+    on jobs of at least 32 x 148 x 8 tiles, more than the other tests stack: every pixel and the clip totals of a
+    1.2 M pixel job against the oracle, with the built-in schedules"""
+    p = 37888 * 32 + 4096 + 17
+    frames = O.synth_frames(n, 12345 * n, p)
+    for mode, weighted in (("sigma", False), ("sigma", True), ("winsor", False), ("linfit", False)):
+        check_against_oracle(ctx, frames, mode, weighted)
+        check_against_oracle(ctx, frames, mode, weighted, 1.0, 2.0)
