@@ -952,7 +952,8 @@ def main():
         args.warmup = 3
     if args.config == "c3":
         from tools.bench_c3 import run_c3, run_c3_multi
-        return run_c3_multi(args) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else run_c3(args)
+        multi = int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("NL_C3_MULTI") == "1"   # (the N-GPU path on one rank: a check)
+        return run_c3_multi(args) if multi else run_c3(args)
     cfg = WORKLOADS[args.config]
     if args.verify_rows is None:
         args.verify_rows = {"c4": 8, "c5": 32}.get(args.config, 16)
