@@ -172,3 +172,50 @@ def test_sigma_goal_seek_state_machine_matches_the_python_restatement(mode):
             assert got[2] == len(trace)
         else:
             assert got[4] == [] and got[:2] == (0.0, 0.0)
+
+
+def test_go_shims_only_use_declared_symbols_with_the_declared_arity():
+    """integration/go cannot be compiled here (no Go toolchain): at least every C.nl_* the cgo files name must be declared
+    in include/nightlight_cuda.h, and every call must pass as many arguments as the declaration has parameters"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "nightlight_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(nl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        params = m.group(2).strip()
+        decl[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    types = set(re.findall(r"\b(nl_[a-z0-9_]+)\b", header))
+
+    def call_args(src, start):
+        """number of top-level arguments of the call whose '(' is at src[start]"""
+        depth, n, seen = 0, 0, False
+        for ch in src[start:]:
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return n + (1 if seen else 0)
+            elif ch == "," and depth == 1:
+                n += 1
+            elif depth >= 1 and not ch.isspace():
+                seen = True
+        raise AssertionError("unbalanced call")
+
+    files = glob.glob(os.path.join(root, "integration", "go", "**", "*.go"), recursive=True)
+    assert files
+    calls = 0
+    for f in files:
+        src = open(f).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        for m in re.finditer(r"\bC\.(nl_[a-zA-Z0-9_]+)", src):
+            name = m.group(1)
+            assert name in types, (os.path.basename(f), name, "not in include/nightlight_cuda.h")
+            rest = src[m.end():]
+            if name in decl and rest.lstrip().startswith("("):
+                got = call_args(src, m.end() + (len(rest) - len(rest.lstrip())))
+                assert got == decl[name], (os.path.basename(f), name, "passes %d arguments, declared with %d" % (got, decl[name]))
+                calls += 1
+    assert calls >= 10
